@@ -1,0 +1,203 @@
+/*
+ * tiler_slider.h -- C-ABI of libtiler_slider.so, the B200 (sm_100a) batched Tiler-Slider
+ * step path.
+ *
+ * The reference (AnimeshSinha1309/tiler-slider) is pure Python and has no FFI boundary; the
+ * path sits behind two classes, GameState (explainrl/environment/state.py:18-222) and
+ * TilerSliderEnv (explainrl/environment/environment.py:14-194).  Each entry point below
+ * names the reference code whose results it reproduces; INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer named d_* (or inside a ts_*_args struct, unless marked host) is a DEVICE
+ *    pointer into caller-owned memory (PyTorch tensors in this repo).  The library
+ *    allocates nothing persistent except inside ts_host_ctx.
+ *  - Calls are asynchronous on the given cudaStream_t (void*; 0 = legacy default stream),
+ *    except ts_step_host which synchronises before it returns.
+ *  - Return value: 0 = success; negative = argument error (TS_E_*); positive = cudaError_t
+ *    from the launch.  ts_last_error_string() describes the last failure of the calling
+ *    thread.  No global mutable state: re-entrant across streams and devices (the caller
+ *    selects the device).
+ *  - There is no CPU fallback anywhere in this library.
+ *
+ * Packed layout (struct-of-arrays, environment index innermost):
+ *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.
+ *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = (row<<4)|col of tile
+ *    i, unused bytes zero.  Arrays: pos (in/out), init, targets (ordered mode).
+ *  - board: bitboard of ts_board_bytes(S) = ceil(S*S/8) bytes per env, bit r*S+c set =
+ *    blocked (walls) or target cell (targets, set mode), little endian, split into byte
+ *    planes of width 16 (repeated), 8, 4, 2, 1 -- widest first; plane k of a buffer starts at
+ *    byte offset ts_plane_offset(nb,k)*capacity and holds one element per env.
+ *  - step_count: uint8 per env when max_steps <= 255 (count_bytes = 1), else int32
+ *    (count_bytes = 4).
+ *  - actions: uint8 per env, 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (state.py:31-34).
+ */
+#ifndef TILER_SLIDER_H
+#define TILER_SLIDER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TS_VERSION 100          /* 0.1.0 */
+#define TS_CAP_ALIGN 128
+#define TS_MAX_SIZE 16
+#define TS_MAX_TILES 8
+
+/* flag bits of the per-env status byte */
+#define TS_F_DONE 1u      /* environment.py:133-141  done = is_won or step_count >= max_steps */
+#define TS_F_WON 2u       /* info['is_won'] / info['success']  (state.py:172-186)            */
+#define TS_F_INVALID 4u   /* info['invalid_move']: no tile moved (environment.py:129)         */
+#define TS_F_TIMEOUT 8u   /* info['timeout'] (environment.py:139-141)                         */
+#define TS_F_STALE 16u    /* stepped while already done without auto_reset: frozen, no-op
+                             (the reference raises RuntimeError, environment.py:113-114)      */
+
+/* goal modes */
+#define TS_GOAL_ORDERED 0 /* multi_color=True : tile i on target i (state.py:183-184); targets
+                             are packed position words                                        */
+#define TS_GOAL_SET 1     /* multi_color=False: occupancy == target set (state.py:185-186);
+                             targets are a bitboard in the plane layout                       */
+
+/* error codes */
+#define TS_E_BAD_SIZE (-1)
+#define TS_E_BAD_TILES (-2)
+#define TS_E_BAD_CAPACITY (-3)
+#define TS_E_NULL_POINTER (-4)
+#define TS_E_MISALIGNED (-5)
+#define TS_E_BAD_RANGE (-6)
+#define TS_E_UNSUPPORTED (-7)
+#define TS_E_BAD_ARGUMENT (-8)
+
+int ts_version(void);
+const char *ts_last_error_string(void);
+
+/* layout queries (pure host arithmetic) */
+int ts_pos_bytes(int n_tiles);
+int ts_board_bytes(int size);
+int ts_plane_count(int n_bytes);
+int ts_plane_width(int n_bytes, int k);
+int ts_plane_offset(int n_bytes, int k);
+/* 1 if ts_step has a specialised kernel for (size, n_tiles), else 0 */
+int ts_supported(int size, int n_tiles);
+
+/* ---------------------------------------------------------------------------------------
+ * K1 ts_encode: dense per-env description -> packed layout.
+ * Reproduces GameState.__init__ (state.py:61-73): is_blocked grid + location lists.
+ *   d_blocked  u8 [n_envs][size*size]  nonzero = blocked cell
+ *   d_tiles    u8 [n_envs][n_tiles][2] (row, col)
+ *   d_targets  u8 [n_envs][n_targets][2]
+ * Writes walls planes, init + pos position words, targets (ordered: position word, requires
+ * n_targets == n_tiles; set: bitboard planes, any n_targets), step_count = 0.
+ * Environments are written at [first_env, first_env + n_envs).
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_encode_args {
+    int32_t size, n_tiles, n_targets, goal_mode;
+    int64_t first_env, n_envs, capacity;
+    const uint8_t *d_blocked, *d_tiles, *d_targets;
+    uint8_t *d_walls, *d_targets_packed, *d_init, *d_pos;
+} ts_encode_args;
+int ts_encode(const ts_encode_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K0 ts_synth: synthetic puzzles generated on the device in the packed layout.
+ * Same recipe as TilerSliderEnvFactory.create_simple_env (environment.py:221-226): a
+ * uniformly random arrangement of distinct cells, the first n_walls blocked, the next
+ * n_tiles tiles, the next n_tiles targets (always well formed).  The random stream is a
+ * counter-based hash of (seed, global env index = env_index_base + local index), NOT
+ * numpy's Mersenne Twister, so puzzles differ from create_simple_env(seed=...) but are
+ * independent of how environments are sharded across GPUs.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_synth_args {
+    int32_t size, n_tiles, n_walls, goal_mode;
+    int64_t first_env, n_envs, capacity, env_index_base;
+    uint64_t seed;
+    uint8_t *d_walls, *d_targets_packed, *d_init, *d_pos;
+} ts_synth_args;
+int ts_synth(const ts_synth_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2 ts_step: one environment step for envs [first_env, first_env+n_envs) (first_env a
+ * multiple of 4).  Fuses GameState.move (state.py:120-170), is_won (state.py:172-186) and
+ * the bookkeeping of TilerSliderEnv.step (environment.py:119-143): invalid_move, win ->
+ * done, step counter, timeout; plus (new in this repo) reward and optional auto-reset
+ * (TilerSliderEnv.reset, environment.py:89-97: positions <- init, step_count <- 0).
+ *
+ *   reward  = won ? r_win : invalid_move ? r_invalid : r_step      (stale envs: 0)
+ *   d_flags : TS_F_* bits.  With auto_reset = 0 it is read first: an env whose DONE bit is
+ *             set is frozen and reports DONE|STALE.  With auto_reset = 1 it is write-only
+ *             and may be NULL.
+ *   d_done  : 0/1 byte per env (may be NULL if d_flags is given).
+ *   d_terminal_pos : optional position words, written for a 4-env group whenever one of its
+ *             envs finished this step: the positions after the move, before the reset.
+ *   never_win: 1 when the goal can never be met (ordered mode with len(targets) !=
+ *             len(tiles), state.py:183-184).
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_step_args {
+    int32_t size, n_tiles, goal_mode, never_win;
+    int64_t first_env, n_envs, capacity;
+    const uint8_t *d_walls, *d_targets_packed, *d_init;
+    uint8_t *d_pos;
+    void *d_step_count;
+    int32_t count_bytes, max_steps, auto_reset, reserved0;
+    const uint8_t *d_actions;
+    float r_win, r_step, r_invalid, reserved1;
+    float *d_reward;
+    uint8_t *d_done, *d_flags, *d_terminal_pos;
+} ts_step_args;
+int ts_step(const ts_step_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3 ts_observe: dense observation, GameState.get_state_array (state.py:188-211).
+ *   d_obs f32 [n_envs][size][size][3] (HWC): ch0 blocked, ch1 tile index+1 (ordered mode) or
+ *   1 (set mode), ch2 target index+1 or 1.  In set mode targets come from the bitboard.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_observe_args {
+    int32_t size, n_tiles, goal_mode, reserved;
+    int64_t first_env, n_envs, capacity;
+    const uint8_t *d_walls, *d_targets_packed, *d_pos;
+    float *d_obs;
+} ts_observe_args;
+int ts_observe(const ts_observe_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ts_valid_moves: bit d of d_mask[env] set when move d changes any tile position
+ * (TilerSliderEnv.get_valid_moves, environment.py:149-171).
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_valid_args {
+    int32_t size, n_tiles;
+    int64_t first_env, n_envs, capacity;
+    const uint8_t *d_walls, *d_pos;
+    uint8_t *d_mask;
+} ts_valid_args;
+int ts_valid_moves(const ts_valid_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ts_goal_check: d_won[env] = 1 when the CURRENT positions meet the goal
+ * (GameState.is_won, state.py:172-186), without moving.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_goal_args {
+    int32_t size, n_tiles, goal_mode, never_win;
+    int64_t first_env, n_envs, capacity;
+    const uint8_t *d_targets_packed, *d_pos;
+    uint8_t *d_won;
+} ts_goal_args;
+int ts_goal_check(const ts_goal_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ts_step_host: the same step through HOST buffers (the call a host-side driver makes):
+ * h_actions (pinned) -> device, ts_step, reward/done -> h_reward/h_done (pinned), pipelined in
+ * chunks over the context's streams; returns after everything has landed.
+ * a->d_actions/d_reward/d_done must still point at device staging of n_envs elements.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_host_ctx ts_host_ctx;
+int ts_host_ctx_create(ts_host_ctx **out, int n_streams);
+int ts_host_ctx_destroy(ts_host_ctx *ctx);
+int ts_step_host(ts_host_ctx *ctx, const ts_step_args *a, const uint8_t *h_actions, float *h_reward,
+                 uint8_t *h_done, int64_t chunk_envs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TILER_SLIDER_H */

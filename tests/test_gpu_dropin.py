@@ -1,0 +1,148 @@
+"""Drop-in surface on the GPU: GameState / TilerSliderEnv / TilerSliderEnvFactory with the
+reference's names, signatures, return shapes and error behaviour (environment.py:14-288,
+state.py:18-222), checked against the golden fixtures and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.test_oracle_golden import MOVES, SEQ1, SEQ2, SCENARIO_PUZZLE, render
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import tiler_slider_b200 as t
+    t.lib()
+    return t
+
+
+class Level:  # stands in for ImageLoader.ImageProcessed (dataloader.py:21-27)
+    def __init__(self, size, blocked, tiles, targets, multi):
+        self.size, self.blocked_locations, self.initial_locations = size, blocked, tiles
+        self.target_locations, self.multiple_colors = targets, multi
+
+
+def env_render(env):
+    return render(env.size, [tuple(x) for x in np.argwhere(env.state.is_blocked)], env.state.current_locations,
+                  env.state.target_locations, env.multi_color)
+
+
+@pytest.mark.parametrize("seq", [SEQ1, SEQ2])
+def test_user_scenarios_through_from_level(ts, seq):
+    """tests/test_user_scenarios.py:22-128 of the reference, board string after every move."""
+    p = SCENARIO_PUZZLE
+    env = ts.TilerSliderEnv.from_level(Level(4, p["blocked"], p["tiles"], p["targets"], True))
+    obs = env.reset()
+    assert obs.shape == (4, 4, 3) and obs.dtype == np.float32
+    assert env_render(env) == "A..a\nX...\n...X\nB.b."
+    for i, (mv, board, won) in enumerate(seq):
+        out = env.step(ts.GameState.Move.from_char(mv))
+        assert isinstance(out, tuple) and len(out) == 3
+        obs, done, info = out
+        assert env_render(env) == board
+        assert done is won and info["is_won"] is won and info["step_count"] == i
+        assert ("success" in info) == won
+    if seq is SEQ2:
+        assert [s[1] for s in seq][3] == [s[1] for s in seq][4]
+
+
+def test_scenarios_fixture_info_dicts(ts, golden_scenarios):
+    for rec in golden_scenarios:
+        p = rec["puzzle"]
+        env = ts.TilerSliderEnv(p["size"], [tuple(x) for x in p["blocked"]], [tuple(x) for x in p["tiles"]],
+                                [tuple(x) for x in p["targets"]], p["multi_color"], max_steps=p.get("max_steps", 100))
+        env.reset()
+        for step in rec["steps"]:
+            obs, done, info = env.step(ts.Move.from_char(step["move"]))
+            assert [list(map(int, x)) for x in env.state.current_locations] == step["positions"]
+            assert done == step["done"] and info == step["info"]
+            assert float(obs.sum()) == step["obs_sum"]
+
+
+def test_errors_and_bookkeeping(ts):
+    """RuntimeError after done (environment.py:113-114), TypeError on a plain int (:116-117),
+    timeout exactly on the max_steps-th step (:138-141), no win at reset."""
+    env = ts.TilerSliderEnv(3, [], [(1, 1)], [(1, 1)], False, max_steps=2)
+    env.reset()
+    assert env.done is False and env.step_count == 0
+    with pytest.raises(TypeError, match="Action must be a GameState.Move enum"):
+        env.step(0)
+    obs, done, info = env.step(ts.Move.UP)
+    assert not done and info == {"is_won": False, "step_count": 0, "invalid_move": False}
+    obs, done, info = env.step(ts.Move.UP)
+    assert done and info["timeout"] is True and info["invalid_move"] is True and "success" not in info
+    with pytest.raises(RuntimeError, match="Episode is done"):
+        env.step(ts.Move.DOWN)
+    env.reset()
+    assert env.step_count == 0 and not env.done
+    fresh = ts.TilerSliderEnv(3, [], [(0, 0)], [(2, 2)])
+    with pytest.raises(AttributeError):
+        fresh.step(ts.Move.UP)
+    assert fresh.get_valid_moves() == [] and fresh.get_info() == {"initialized": False}
+    fresh.reset()
+    info = fresh.get_info()
+    assert info["initialized"] and info["num_tiles"] == 1 and info["valid_moves"] == [ts.Move.DOWN, ts.Move.RIGHT]
+    fresh.close()
+    assert fresh.state is None
+
+
+def test_gamestate_surface(ts, golden_misc):
+    for t in golden_misc["slide_tables"]:
+        st = ts.GameState(t["size"], [tuple(b) for b in t["blocked"]], [(0, 0)], [(t["size"] - 1,) * 2], False)
+        assert st.is_blocked.shape == (t["size"],) * 2 and st.is_blocked.dtype == bool
+        assert np.array_equal(st.move_to, np.array(t["move_to"]))
+    for c in golden_misc["collisions"]:
+        st = ts.GameState(c["size"], [tuple(b) for b in c["blocked"]], [tuple(x) for x in c["tiles"]],
+                          [(0, 0)] * len(c["tiles"]), False)
+        st.move(ts.Move.from_char(c["move"]))
+        assert [list(map(int, x)) for x in st.current_locations] == c["after"]
+    for w in golden_misc["win_logic"]:
+        if len(w["tiles"]) > 0 and w["multi_color"] and len(w["tiles"]) != len(w["targets"]):
+            continue
+        st = ts.GameState(3, [], [tuple(x) for x in w["tiles"]], [tuple(x) for x in w["targets"]], w["multi_color"])
+        assert st.is_won() == w["is_won"], w
+    for o in golden_misc["observations"]:
+        env = ts.TilerSliderEnvFactory.create_from_string(o["text"], multi_color=o["multi_color"])
+        assert np.array_equal(env.reset(), np.array(o["obs"], dtype=np.float32))
+    for v in golden_misc["valid_moves"]:
+        env = ts.TilerSliderEnvFactory.create_from_string(v["text"], multi_color=v["multi_color"])
+        env.reset()
+        assert [m.value for m in env.get_valid_moves()] == v["valid"]
+    st = ts.GameState(5, [(2, 2)], [(0, 0), (4, 4)], [(4, 0), (0, 4)], True)
+    cp = st.copy()
+    cp.move(ts.Move.DOWN)
+    assert st.current_locations == [(0, 0), (4, 4)] and cp.current_locations == [(4, 0), (4, 4)]
+    assert ts.Move.from_char("u") is ts.Move.UP and ts.Move.from_int(3) is ts.Move.RIGHT and ts.Move.from_char("q") is None
+
+
+def test_factory(ts, golden_misc):
+    for f in golden_misc["factory"]:
+        env = ts.TilerSliderEnvFactory.create_simple_env(**f["kwargs"])
+        assert [list(map(int, x)) for x in env.blocked_locations] == f["blocked"]
+        assert [list(map(int, x)) for x in env.initial_locations] == f["tiles"]
+        assert [list(map(int, x)) for x in env.target_locations] == f["targets"]
+        assert env.multi_color is False
+    for g in golden_misc["grammar"]:
+        env = ts.TilerSliderEnvFactory.create_from_string(g["text"])
+        assert env.size == g["size"]
+        assert [list(x) for x in env.blocked_locations] == g["blocked"]
+        assert [list(x) for x in env.initial_locations] == g["tiles"]
+        assert [list(x) for x in env.target_locations] == g["targets"]
+
+
+def test_full_episode_matches_oracle(ts):
+    rng = np.random.default_rng(3)
+    for seed in range(6):
+        env = ts.TilerSliderEnvFactory.create_simple_env(size=6, num_tiles=3, num_obstacles=6, seed=seed)
+        env.max_steps = 40
+        st = orc.OracleState(6, env.blocked_locations, env.initial_locations, env.target_locations, False)
+        env.reset()
+        for k in range(40):
+            mv = int(rng.integers(0, 4))
+            obs, done, info = env.step(ts.Move(mv))
+            won = st.move(mv)
+            assert [tuple(map(int, x)) for x in env.state.current_locations] == st.current_locations
+            assert info["is_won"] == won and np.array_equal(obs, st.get_state_array())
+            if done:
+                break

@@ -1,0 +1,263 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via BatchedTilerSliderEnv) against the
+CPU oracle and the reference-generated golden fixtures.  Integer / byte work: the bar is
+bit-exact equality everywhere; the float32 observation holds small integers, so it is
+compared with exact equality too (no tolerance).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.helpers import random_puzzles
+
+pytestmark = pytest.mark.gpu
+
+F_DONE, F_WON, F_INVALID, F_TIMEOUT, F_STALE = 1, 2, 4, 8, 16
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import tiler_slider_b200 as t
+    assert torch.cuda.is_available()
+    t.lib()
+    return t
+
+
+def run_gpu(ts, S, multi, blocked, tiles, targets, actions, max_steps, auto_reset):
+    """Drive the batch env with the action matrix; return post-move/pre-reset positions,
+    flags, pre-increment counts and rewards per step, like the oracle's rollout."""
+    env = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=max_steps,
+                                               auto_reset=auto_reset, track_terminal=True)
+    K, N = actions.shape
+    T = tiles.shape[1]
+    acts = torch.as_tensor(actions).cuda()
+    pos = np.zeros((K, N, T, 2), np.int16)
+    flags = np.zeros((K, N), np.uint8)
+    count = np.zeros((K, N), np.int32)
+    reward = np.zeros((K, N), np.float32)
+    for k in range(K):
+        before = env.step_count.to(torch.int32).clone()
+        state, r, d = env.step(acts[k])
+        f = env.flags
+        assert torch.equal(d, (f & F_DONE) != 0)
+        post = env.positions()
+        if auto_reset:
+            term = env.positions(env.terminal_pos)
+            post = torch.where(d[:, None, None], term, post)
+        pos[k] = post.cpu().numpy()
+        flags[k] = f.cpu().numpy()
+        count[k] = before.cpu().numpy()
+        reward[k] = r.cpu().numpy()
+    return dict(pos=pos, flags=flags, count=count, reward=reward,
+                final_pos=env.positions().cpu().numpy().astype(np.int16),
+                final_count=env.step_count.to(torch.int32).cpu().numpy())
+
+
+def assert_same(got, want, tag=""):
+    for key in ("pos", "flags", "count", "reward", "final_pos", "final_count"):
+        if key in want:
+            assert np.array_equal(got[key], want[key]), f"{tag}: {key} differs"
+
+
+def test_golden_rollouts(ts, golden_rollouts):
+    """Reference-recorded rollouts (tests/golden/rollouts.npz) replayed on the GPU."""
+    n = 0
+    for rec in golden_rollouts:
+        if not ts.lib().ts_supported(rec["S"], rec["T"]):
+            continue
+        got = run_gpu(ts, rec["S"], rec["multi"], rec["blocked"], rec["tiles"], rec["targets"], rec["actions"],
+                      rec["max_steps"], True)
+        assert np.array_equal(got["pos"], rec["pos"]), rec["tag"]
+        assert np.array_equal(got["flags"], rec["flags"]), rec["tag"]
+        assert np.array_equal(got["count"], rec["count"]), rec["tag"]
+        n += rec["flags"].size
+    assert n > 10000
+
+
+SHAPES = [  # S, T, W, multi, N, K, max_steps
+    (5, 1, 5, False, 8192, 128, 100),      # config 2
+    (6, 4, 8, True, 8192, 128, 100),       # config 3
+    (6, 4, 8, False, 4096, 96, 100),
+    (4, 2, 2, True, 4096, 64, 7),
+    (3, 3, 1, False, 2048, 64, 5),
+    (2, 2, 0, True, 1024, 32, 3),
+    (1, 1, 0, False, 256, 8, 2),
+    (5, 4, 3, True, 4096, 64, 300),        # int32 step counter
+    (6, 8, 6, True, 4096, 64, 100),
+    (6, 3, 0, False, 2048, 64, 100),
+    (7, 5, 10, True, 4096, 64, 50),
+    (8, 8, 12, True, 4096, 64, 100),
+    (8, 6, 20, False, 2048, 64, 13),
+    (7, 7, 4, False, 2048, 64, 100),
+]
+
+
+@pytest.mark.parametrize("S,T,W,multi,N,K,max_steps", SHAPES)
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_random_vs_oracle(ts, S, T, W, multi, N, K, max_steps, auto_reset):
+    """>= 1e6 checked env-steps for the bench shapes: positions per tile, is_won,
+    invalid_move, timeout, done, stale, pre-increment step_count, reward."""
+    if not ts.lib().ts_supported(S, T):
+        pytest.skip("shape not built")
+    rng = np.random.default_rng(1000 * S + 10 * T + W + (7 if multi else 0))
+    blocked, tiles, targets = random_puzzles(rng, N, S, T, W) if W + 2 * T <= S * S else crowded(rng, N, S, T, W)
+    actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+    want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=auto_reset)
+    got = run_gpu(ts, S, multi, blocked, tiles, targets, actions, max_steps, auto_reset)
+    assert_same(got, want, f"S{S}T{T}")
+
+
+def crowded(rng, N, S, T, W):
+    """Boards too full for disjoint tiles and targets: targets drawn independently."""
+    blocked, tiles, _ = random_puzzles(rng, N, S, T, W) if W + T <= S * S else (None, None, None)
+    _, targets, _ = random_puzzles(rng, N, S, T, 0)
+    return blocked, tiles, targets
+
+
+def test_targets_under_tiles_and_crowded(ts):
+    rng = np.random.default_rng(5)
+    for S, T, W, multi in [(1, 1, 0, False), (2, 2, 1, True), (3, 8, 0, False), (3, 8, 1, True), (4, 8, 8, False)]:
+        N, K = 512, 24
+        blocked, tiles, targets = crowded(rng, N, S, T, W)
+        actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+        want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=9, auto_reset=True)
+        got = run_gpu(ts, S, multi, blocked, tiles, targets, actions, 9, True)
+        assert_same(got, want, f"crowded S{S}T{T}")
+
+
+def test_set_goal_with_duplicate_and_missing_targets(ts):
+    """Single colour is set equality (state.py:185-186): duplicate targets collapse, a target
+    count different from the tile count can never (or only by collapse) be met."""
+    S = 3
+    blocked = np.zeros((2, 9), np.uint8)
+    tiles = np.array([[[0, 0]], [[0, 0]]], np.uint8)
+    targets = np.array([[[0, 2], [0, 2]], [[0, 2], [2, 2]]], np.uint8)
+    acts = np.array([[3, 3], [1, 1]], np.uint8)
+    want = orc.rollout(S, False, blocked, tiles, targets, acts)
+    got = run_gpu(ts, S, False, blocked, tiles, targets, acts, 100, False)
+    assert_same(got, want)
+    assert want["flags"][0, 0] & F_WON and not (want["flags"][:, 1] & F_WON).any()
+
+
+def test_ordered_goal_length_mismatch_never_wins(ts):
+    blocked = np.zeros((1, 9), np.uint8)
+    tiles = np.array([[[0, 0]]], np.uint8)
+    targets = np.array([[[0, 2], [2, 2]]], np.uint8)
+    acts = np.array([[3], [1]], np.uint8)
+    want = orc.rollout(3, True, blocked, tiles, targets, acts)
+    got = run_gpu(ts, 3, True, blocked, tiles, targets, acts, 100, False)
+    assert_same(got, want)
+    assert not (got["flags"] & F_WON).any()
+
+
+def test_observation_valid_moves_goal(ts):
+    rng = np.random.default_rng(11)
+    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (4, 2, 2, True), (8, 8, 10, True)]:
+        N, K = 256, 12
+        blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
+        actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+        env = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=1000)
+        states = []
+        for e in range(N):
+            b = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+            states.append(orc.OracleState(S, b, tiles[e].tolist(), targets[e].tolist(), multi))
+        for k in range(K + 1):
+            obs = env.observe().cpu().numpy()
+            vm = env.valid_moves().cpu().numpy()
+            won = env.goal_check().cpu().numpy()
+            for e in range(N):
+                assert np.array_equal(obs[e], states[e].get_state_array())
+                assert [d for d in range(4) if vm[e] >> d & 1] == states[e].valid_moves()
+                assert bool(won[e]) == states[e].is_won()
+            if k < K:
+                fl = env.raw_move(torch.as_tensor(actions[k]).cuda()).cpu().numpy()
+                for e in range(N):
+                    w = states[e].move(int(actions[k, e]))
+                    assert bool(fl[e] & F_WON) == w
+
+
+def test_synth_well_formed_and_shard_invariant(ts):
+    S, T, W = 6, 4, 8
+    full = ts.BatchedTilerSliderEnv.synthetic(4096, S, T, W, True, seed=77)
+    blocked = full.blocked_cells().cpu().numpy()
+    pos = full.positions().cpu().numpy().astype(int)
+    tg = full.target_positions().cpu().numpy().astype(int)
+    assert (blocked.sum(1) == W).all()
+    cells = pos[..., 0] * S + pos[..., 1]
+    tcells = tg[..., 0] * S + tg[..., 1]
+    for e in range(0, 4096, 37):
+        occupied = set(np.flatnonzero(blocked[e])) | set(cells[e]) | set(tcells[e])
+        assert len(occupied) == W + 2 * T
+    # the same global env index gives the same puzzle whatever the shard
+    part = ts.BatchedTilerSliderEnv.synthetic(1024, S, T, W, True, seed=77, env_index_base=2048)
+    assert torch.equal(part.pos, full.pos[2048:3072])
+    assert torch.equal(part.blocked_cells(), full.blocked_cells()[2048:3072])
+    other = ts.BatchedTilerSliderEnv.synthetic(1024, S, T, W, True, seed=78)
+    assert not torch.equal(other.pos, full.pos[:1024])
+    # set mode: targets as a bitboard of exactly T cells, disjoint from tiles and walls
+    single = ts.BatchedTilerSliderEnv.synthetic(512, S, T, W, False, seed=3)
+    tb = single.target_positions().cpu().numpy()
+    assert (tb.sum(1) == T).all() and not (tb & single.blocked_cells().cpu().numpy()).any()
+
+
+def test_synthetic_rollout_vs_oracle(ts):
+    """The bench workload itself: device-generated puzzles decoded to the host and replayed by
+    the oracle (config 2 and config 3 shapes)."""
+    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True)]:
+        N, K = 8192, 128
+        env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, seed=1002, max_steps=100, auto_reset=True,
+                                                 track_terminal=True)
+        blocked = env.blocked_cells().cpu().numpy().astype(np.uint8)
+        tiles = env.positions().cpu().numpy()
+        if multi:
+            targets = env.target_positions().cpu().numpy()
+        else:
+            tgt_cells = env.target_positions().cpu().numpy()
+            targets = np.stack([np.flatnonzero(r) for r in tgt_cells])
+            targets = np.stack([targets // S, targets % S], -1).astype(np.uint8)
+        g = torch.Generator(device="cuda").manual_seed(2002)
+        actions = torch.randint(0, 4, (K, N), dtype=torch.uint8, device="cuda", generator=g)
+        want = orc.rollout(S, multi, blocked, tiles, targets, actions.cpu().numpy(), max_steps=100, auto_reset=True)
+        for k in range(K):
+            _, r, d = env.step(actions[k])
+            post = torch.where(d[:, None, None], env.positions(env.terminal_pos), env.positions())
+            assert np.array_equal(post.cpu().numpy(), want["pos"][k])
+            assert np.array_equal(env.flags.cpu().numpy(), want["flags"][k])
+            assert np.array_equal(r.cpu().numpy(), want["reward"][k])
+
+
+def test_step_host_matches_step(ts):
+    S, T, W, N = 6, 4, 8, 50_000
+    a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=9, auto_reset=True)
+    b = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=9, auto_reset=True)
+    h_act = torch.empty(N, dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+    rng = np.random.default_rng(1)
+    for k in range(20):
+        h_act.copy_(torch.from_numpy(rng.integers(0, 4, N, dtype=np.uint8)))
+        _, r, d = a.step(h_act.cuda())
+        b.step_host(h_act, h_rew, h_done, chunk_envs=8192)
+        assert torch.equal(a.pos, b.pos)
+        assert torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done.bool())
+
+
+def test_argument_errors(ts):
+    import ctypes as C
+    from tiler_slider_b200 import _lib
+    env = ts.BatchedTilerSliderEnv.synthetic(256, 5, 1, 5, False)
+    a = env._step_args(env._actions.data_ptr())
+    a.capacity = 100
+    assert ts.lib().ts_step(C.byref(a), None) == -3
+    a = env._step_args(env._actions.data_ptr() + 1)
+    assert ts.lib().ts_step(C.byref(a), None) == -5
+    a = env._step_args(env._actions.data_ptr())
+    a.size = 17
+    assert ts.lib().ts_step(C.byref(a), None) == -1
+    assert b"size" in ts.lib().ts_last_error_string()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(3, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        ts.BatchedTilerSliderEnv.from_puzzles([ts.Puzzle(3, [(0, 0)], [(0, 0)], [(1, 1)])])
+    with pytest.raises(ValueError):
+        ts.BatchedTilerSliderEnv.from_puzzles([ts.Puzzle(3, [], [(0, 0), (0, 0)], [(1, 1), (2, 2)])])

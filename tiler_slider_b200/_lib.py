@@ -1,0 +1,127 @@
+"""ctypes binding of libtiler_slider.so (C-ABI declared in include/tiler_slider.h).
+
+The library is the product: if it is missing, import of anything that computes fails
+loudly -- there is no CPU or PyTorch fallback.  `build()` compiles it in-tree with nvcc for
+sm_100a (tiler_slider_b200/csrc/Makefile).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtiler_slider.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+CAP_ALIGN = 128
+MAX_SIZE = 16
+MAX_TILES = 8
+F_DONE, F_WON, F_INVALID, F_TIMEOUT, F_STALE = 1, 2, 4, 8, 16
+GOAL_ORDERED, GOAL_SET = 0, 1
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class EncodeArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("n_targets", _i32), ("goal_mode", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64),
+                ("d_blocked", _vp), ("d_tiles", _vp), ("d_targets", _vp),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_pos", _vp)]
+
+
+class SynthArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("n_walls", _i32), ("goal_mode", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64), ("env_index_base", _i64),
+                ("seed", C.c_uint64),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_pos", _vp)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("never_win", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_pos", _vp),
+                ("d_step_count", _vp),
+                ("count_bytes", _i32), ("max_steps", _i32), ("auto_reset", _i32), ("reserved0", _i32),
+                ("d_actions", _vp),
+                ("r_win", _f32), ("r_step", _f32), ("r_invalid", _f32), ("reserved1", _f32),
+                ("d_reward", _vp), ("d_done", _vp), ("d_flags", _vp), ("d_terminal_pos", _vp)]
+
+
+class ObserveArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("reserved", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_pos", _vp), ("d_obs", _vp)]
+
+
+class ValidArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64),
+                ("d_walls", _vp), ("d_pos", _vp), ("d_mask", _vp)]
+
+
+class GoalArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("never_win", _i32),
+                ("first_env", _i64), ("n_envs", _i64), ("capacity", _i64),
+                ("d_targets_packed", _vp), ("d_pos", _vp), ("d_won", _vp)]
+
+
+# every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ts_version": (C.c_int, []),
+    "ts_last_error_string": (C.c_char_p, []),
+    "ts_pos_bytes": (C.c_int, [C.c_int]),
+    "ts_board_bytes": (C.c_int, [C.c_int]),
+    "ts_plane_count": (C.c_int, [C.c_int]),
+    "ts_plane_width": (C.c_int, [C.c_int, C.c_int]),
+    "ts_plane_offset": (C.c_int, [C.c_int, C.c_int]),
+    "ts_supported": (C.c_int, [C.c_int, C.c_int]),
+    "ts_encode": (C.c_int, [C.POINTER(EncodeArgs), _vp]),
+    "ts_synth": (C.c_int, [C.POINTER(SynthArgs), _vp]),
+    "ts_step": (C.c_int, [C.POINTER(StepArgs), _vp]),
+    "ts_observe": (C.c_int, [C.POINTER(ObserveArgs), _vp]),
+    "ts_valid_moves": (C.c_int, [C.POINTER(ValidArgs), _vp]),
+    "ts_goal_check": (C.c_int, [C.POINTER(GoalArgs), _vp]),
+    "ts_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "ts_host_ctx_destroy": (C.c_int, [_vp]),
+    "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _i64]),
+}
+
+
+class TilerSliderError(RuntimeError):
+    """A C-ABI call failed (negative: argument error, positive: cudaError_t)."""
+
+
+def build(force: bool = False, jobs: int | None = None) -> str:
+    """Compile libtiler_slider.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, f"-j{jobs or os.cpu_count() or 4}"]
+    if force:
+        cmd.append("-B")
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TilerSliderError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+                f"`make -C {CSRC}`.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ts_last_error_string().decode(errors="replace")
+        raise TilerSliderError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,305 @@
+// ts_api.cu -- C-ABI entry points (include/tiler_slider.h), argument validation, and the
+// load-time kernels: K1 ts_encode, K0 ts_synth, K3 ts_observe.
+//
+// Reference map (paths relative to the reference checkout):
+//   ts_encode   explainrl/environment/state.py:61-73        GameState.__init__ (is_blocked + lists)
+//   ts_synth    explainrl/environment/environment.py:221-226 create_simple_env recipe
+//   ts_observe  explainrl/environment/state.py:188-211      get_state_array
+//   ts_step     see ts_step.cuh;  ts_valid_moves see ts_valid.cuh
+#include <cstdarg>
+#include <cstdio>
+#include "ts_common.cuh"
+#include "../../include/tiler_slider.h"
+
+namespace ts {
+#define TS_DECL(S)                                                              \
+    cudaError_t step_dispatch_s##S(const ts_step_args&, cudaStream_t);          \
+    cudaError_t valid_dispatch_s##S(const ts_valid_args&, cudaStream_t);        \
+    cudaError_t goal_dispatch_s##S(const ts_goal_args&, cudaStream_t);
+TS_DECL(1) TS_DECL(2) TS_DECL(3) TS_DECL(4) TS_DECL(5) TS_DECL(6) TS_DECL(7) TS_DECL(8)
+#undef TS_DECL
+
+static thread_local char g_err[256] = "ok";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_result(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_shape(int size, int n_tiles, int64_t first, int64_t n, int64_t cap) {
+    if (size < 1 || size > MAX_SIZE) return fail(TS_E_BAD_SIZE, "size %d outside 1..%d", size, MAX_SIZE);
+    if (n_tiles < 1 || n_tiles > MAX_TILES) return fail(TS_E_BAD_TILES, "n_tiles %d outside 1..%d", n_tiles, MAX_TILES);
+    if (cap <= 0 || cap % CAP_ALIGN != 0) return fail(TS_E_BAD_CAPACITY, "capacity %lld is not a positive multiple of %d", (long long)cap, CAP_ALIGN);
+    if (first < 0 || n < 0 || first % GROUP != 0 || first + n > cap)
+        return fail(TS_E_BAD_RANGE, "env range [%lld, %lld) invalid for capacity %lld (first_env must be a multiple of %d)",
+                    (long long)first, (long long)(first + n), (long long)cap, GROUP);
+    return 0;
+}
+
+// ---- runtime access to the plane layout (load-time kernels only) -----------------------------
+__device__ __forceinline__ size_t board_byte_addr(int nb, size_t cap, size_t env, int byte) {
+    int off = 0;
+    const int np = plane_count(nb);
+    for (int k = 0; k < np; ++k) {
+        const int w = plane_width(nb, k);
+        if (byte < off + w) return (size_t)off * cap + env * (size_t)w + (size_t)(byte - off);
+        off += w;
+    }
+    return 0;
+}
+__device__ __forceinline__ bool board_bit(const uint8_t* base, int nb, size_t cap, size_t env, int bit) {
+    return (base[board_byte_addr(nb, cap, env, bit >> 3)] >> (bit & 7)) & 1;
+}
+
+// ---- K1 encode --------------------------------------------------------------------------------
+__global__ void encode_kernel(const ts_encode_args a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_envs) return;
+    const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
+    const int S = a.size, T = a.n_tiles, NT = a.n_targets, nb = board_bytes(S), pw = pos_bytes(T);
+    const uint8_t* blk = a.d_blocked + (size_t)i * S * S;
+    for (int b = 0; b < nb; ++b) {
+        uint32_t v = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int cell = 8 * b + k;
+            if (cell < S * S && blk[cell]) v |= 1u << k;
+        }
+        a.d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
+    }
+    const uint8_t* tl = a.d_tiles + (size_t)i * T * 2;
+    for (int t = 0; t < pw; ++t) {
+        const uint8_t v = t < T ? (uint8_t)((tl[2 * t] << 4) | (tl[2 * t + 1] & 15)) : 0;
+        a.d_init[env * pw + t] = v;
+        a.d_pos[env * pw + t] = v;
+    }
+    const uint8_t* tg = a.d_targets + (size_t)i * NT * 2;
+    if (a.goal_mode == TS_GOAL_ORDERED) {
+        for (int t = 0; t < pw; ++t)
+            a.d_targets_packed[env * pw + t] = t < NT ? (uint8_t)((tg[2 * t] << 4) | (tg[2 * t + 1] & 15)) : 0;
+    } else {
+        for (int b = 0; b < nb; ++b) {
+            uint32_t v = 0;
+            for (int t = 0; t < NT; ++t) {
+                const int cell = tg[2 * t] * S + tg[2 * t + 1];
+                if ((cell >> 3) == b) v |= 1u << (cell & 7);
+            }
+            a.d_targets_packed[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
+        }
+    }
+}
+
+// ---- K0 synth -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void synth_kernel(const ts_synth_args a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_envs) return;
+    const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
+    const int S = a.size, T = a.n_tiles, W = a.n_walls, nb = board_bytes(S), pw = pos_bytes(T);
+    const int cells = S * S, draws = W + 2 * T;
+    uint64_t rng = a.seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(a.env_index_base + i + 1));
+    splitmix64(rng);
+    uint8_t perm[MAX_SIZE * MAX_SIZE];
+    for (int c = 0; c < cells; ++c) perm[c] = (uint8_t)c;
+    for (int d = 0; d < draws; ++d) {  // partial Fisher-Yates: prefix of a uniform permutation
+        const uint32_t r = (uint32_t)(splitmix64(rng) >> 32);
+        const int j = d + (int)(((uint64_t)r * (uint32_t)(cells - d)) >> 32);
+        const uint8_t t = perm[d];
+        perm[d] = perm[j];
+        perm[j] = t;
+    }
+    uint8_t wbytes[MAX_SIZE * MAX_SIZE / 8], tbytes[MAX_SIZE * MAX_SIZE / 8];
+    for (int b = 0; b < nb; ++b) wbytes[b] = tbytes[b] = 0;
+    for (int d = 0; d < W; ++d) wbytes[perm[d] >> 3] |= (uint8_t)(1u << (perm[d] & 7));
+    for (int t = 0; t < T; ++t) {
+        const int c = perm[W + T + t];
+        tbytes[c >> 3] |= (uint8_t)(1u << (c & 7));
+    }
+    for (int b = 0; b < nb; ++b) a.d_walls[board_byte_addr(nb, cap, env, b)] = wbytes[b];
+    for (int t = 0; t < pw; ++t) {
+        uint8_t v = 0;
+        if (t < T) { const int c = perm[W + t]; v = (uint8_t)(((c / S) << 4) | (c % S)); }
+        a.d_init[env * pw + t] = v;
+        a.d_pos[env * pw + t] = v;
+    }
+    if (a.goal_mode == TS_GOAL_ORDERED) {
+        for (int t = 0; t < pw; ++t) {
+            uint8_t v = 0;
+            if (t < T) { const int c = perm[W + T + t]; v = (uint8_t)(((c / S) << 4) | (c % S)); }
+            a.d_targets_packed[env * pw + t] = v;
+        }
+    } else {
+        for (int b = 0; b < nb; ++b) a.d_targets_packed[board_byte_addr(nb, cap, env, b)] = tbytes[b];
+    }
+}
+
+// ---- K3 observe ---------------------------------------------------------------------------------
+// thread = one cell of one env; a warp writes 32 cells x 3 channels = 384 contiguous bytes.
+__global__ void observe_kernel(const ts_observe_args a) {
+    const int S = a.size, T = a.n_tiles, cells = S * S, nb = board_bytes(S), pw = pos_bytes(T);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_envs * cells) return;
+    const int64_t i = idx / cells;
+    const int cell = (int)(idx - i * cells);
+    const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
+    const uint8_t rc = (uint8_t)(((cell / S) << 4) | (cell % S));
+    const float ch0 = board_bit(a.d_walls, nb, cap, env, cell) ? 1.0f : 0.0f;
+    float ch1 = 0.0f, ch2 = 0.0f;
+    const bool ordered = a.goal_mode == TS_GOAL_ORDERED;
+    for (int t = 0; t < T; ++t)
+        if (a.d_pos[env * pw + t] == rc) ch1 = ordered ? (float)(t + 1) : 1.0f;
+    if (ordered) {
+        for (int t = 0; t < T; ++t)
+            if (a.d_targets_packed[env * pw + t] == rc) ch2 = (float)(t + 1);
+    } else {
+        ch2 = board_bit(a.d_targets_packed, nb, cap, env, cell) ? 1.0f : 0.0f;
+    }
+    float* o = a.d_obs + (size_t)idx * 3;
+    o[0] = ch0; o[1] = ch1; o[2] = ch2;
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" {
+
+int ts_version(void) { return TS_VERSION; }
+const char* ts_last_error_string(void) { return g_err; }
+int ts_pos_bytes(int n_tiles) { return pos_bytes(n_tiles); }
+int ts_board_bytes(int size) { return board_bytes(size); }
+int ts_plane_count(int n_bytes) { return plane_count(n_bytes); }
+int ts_plane_width(int n_bytes, int k) { return plane_width(n_bytes, k); }
+int ts_plane_offset(int n_bytes, int k) { return plane_offset(n_bytes, k); }
+int ts_supported(int size, int n_tiles) { return size >= 1 && size <= 8 && n_tiles >= 1 && n_tiles <= MAX_TILES; }
+
+int ts_encode(const ts_encode_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
+    if (a->goal_mode == TS_GOAL_ORDERED && a->n_targets != a->n_tiles)
+        return fail(TS_E_BAD_TILES, "ordered goal needs n_targets == n_tiles (got %d, %d)", a->n_targets, a->n_tiles);
+    if (a->n_targets < 0 || a->n_targets > MAX_SIZE * MAX_SIZE) return fail(TS_E_BAD_TILES, "n_targets %d", a->n_targets);
+    if (!a->d_blocked || !a->d_tiles || (!a->d_targets && a->n_targets) || !a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos)
+        return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (a->n_envs == 0) return 0;
+    const unsigned blocks = (unsigned)((a->n_envs + 127) / 128);
+    encode_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*a);
+    return cuda_result(cudaGetLastError(), "ts_encode launch");
+}
+
+int ts_synth(const ts_synth_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
+    if (a->n_walls < 0 || a->n_walls + 2 * a->n_tiles > a->size * a->size)
+        return fail(TS_E_BAD_ARGUMENT, "n_walls + 2*n_tiles = %d exceeds the %d cells", a->n_walls + 2 * a->n_tiles, a->size * a->size);
+    if (!a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos) return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (a->n_envs == 0) return 0;
+    const unsigned blocks = (unsigned)((a->n_envs + 127) / 128);
+    synth_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*a);
+    return cuda_result(cudaGetLastError(), "ts_synth launch");
+}
+
+int ts_step(const ts_step_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (!ts_supported(a->size, a->n_tiles)) return fail(TS_E_UNSUPPORTED, "no step kernel for size %d, n_tiles %d", a->size, a->n_tiles);
+    if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
+    if (a->count_bytes != 1 && a->count_bytes != 4) return fail(TS_E_BAD_ARGUMENT, "count_bytes %d (1 or 4)", a->count_bytes);
+    if (a->count_bytes == 1 && a->max_steps > 255) return fail(TS_E_BAD_ARGUMENT, "max_steps %d needs count_bytes 4", a->max_steps);
+    if (!a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos || !a->d_step_count || !a->d_actions || !a->d_reward)
+        return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (!a->d_done && !a->d_flags) return fail(TS_E_NULL_POINTER, "need d_done or d_flags");
+    if (!a->auto_reset && !a->d_flags) return fail(TS_E_NULL_POINTER, "auto_reset=0 needs d_flags (done state is carried there)");
+    const void* ptrs[] = {a->d_walls, a->d_targets_packed, a->d_init, a->d_pos, a->d_step_count, a->d_actions,
+                          a->d_reward, a->d_done, a->d_flags, a->d_terminal_pos};
+    for (const void* p : ptrs)
+        if (p && !aligned16(p)) return fail(TS_E_MISALIGNED, "device pointer %p is not 16-byte aligned", p);
+    if (a->n_envs == 0) return 0;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (a->size) {
+        case 1: e = step_dispatch_s1(*a, st); break;
+        case 2: e = step_dispatch_s2(*a, st); break;
+        case 3: e = step_dispatch_s3(*a, st); break;
+        case 4: e = step_dispatch_s4(*a, st); break;
+        case 5: e = step_dispatch_s5(*a, st); break;
+        case 6: e = step_dispatch_s6(*a, st); break;
+        case 7: e = step_dispatch_s7(*a, st); break;
+        case 8: e = step_dispatch_s8(*a, st); break;
+        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+    }
+    return cuda_result(e, "ts_step launch");
+}
+
+int ts_observe(const ts_observe_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (!a->d_walls || !a->d_targets_packed || !a->d_pos || !a->d_obs) return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (a->n_envs == 0) return 0;
+    const int64_t n = a->n_envs * a->size * a->size;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    observe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    return cuda_result(cudaGetLastError(), "ts_observe launch");
+}
+
+int ts_valid_moves(const ts_valid_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (!ts_supported(a->size, a->n_tiles)) return fail(TS_E_UNSUPPORTED, "no kernel for size %d, n_tiles %d", a->size, a->n_tiles);
+    if (!a->d_walls || !a->d_pos || !a->d_mask) return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (a->n_envs == 0) return 0;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (a->size) {
+        case 1: e = valid_dispatch_s1(*a, st); break;
+        case 2: e = valid_dispatch_s2(*a, st); break;
+        case 3: e = valid_dispatch_s3(*a, st); break;
+        case 4: e = valid_dispatch_s4(*a, st); break;
+        case 5: e = valid_dispatch_s5(*a, st); break;
+        case 6: e = valid_dispatch_s6(*a, st); break;
+        case 7: e = valid_dispatch_s7(*a, st); break;
+        case 8: e = valid_dispatch_s8(*a, st); break;
+        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+    }
+    return cuda_result(e, "ts_valid_moves launch");
+}
+
+int ts_goal_check(const ts_goal_args* a, void* stream) {
+    if (!a) return fail(TS_E_NULL_POINTER, "null args");
+    if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
+    if (!ts_supported(a->size, a->n_tiles)) return fail(TS_E_UNSUPPORTED, "no kernel for size %d, n_tiles %d", a->size, a->n_tiles);
+    if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
+    if (!a->d_targets_packed || !a->d_pos || !a->d_won) return fail(TS_E_NULL_POINTER, "null device pointer");
+    if (a->n_envs == 0) return 0;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (a->size) {
+        case 1: e = goal_dispatch_s1(*a, st); break;
+        case 2: e = goal_dispatch_s2(*a, st); break;
+        case 3: e = goal_dispatch_s3(*a, st); break;
+        case 4: e = goal_dispatch_s4(*a, st); break;
+        case 5: e = goal_dispatch_s5(*a, st); break;
+        case 6: e = goal_dispatch_s6(*a, st); break;
+        case 7: e = goal_dispatch_s7(*a, st); break;
+        case 8: e = goal_dispatch_s8(*a, st); break;
+        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+    }
+    return cuda_result(e, "ts_goal_check launch");
+}
+
+}  // extern "C"

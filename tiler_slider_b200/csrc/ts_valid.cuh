@@ -1,0 +1,111 @@
+// ts_valid.cuh -- per-env mask of the moves that change the state
+// (TilerSliderEnv.get_valid_moves, explainrl/environment/environment.py:149-171), computed
+// by running the slide core for all four directions in registers.
+#pragma once
+#include "ts_common.cuh"
+#include "../../include/tiler_slider.h"
+
+namespace ts {
+
+template <int S, int T>
+__global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_valid_args a) {
+    using BT = BoardTraits<S>;
+    using board_t = typename BT::board_t;
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S), NWORDS = (NB + 3) / 4;
+    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
+    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_groups) return;
+    g += (size_t)a.first_env / GROUP;
+    const size_t e0 = g * GROUP;
+    uint32_t praw[PW];
+    ld_words<PW>(a.d_pos + e0 * PW, praw);
+    BoardGroup<NB> walls;
+    walls.load(a.d_walls, (size_t)a.capacity, g);
+    uint32_t mask4 = 0;
+#pragma unroll
+    for (int e = 0; e < GROUP; ++e) {
+        uint32_t q0[PR], bw[NWORDS];
+        group_elem<PW>(praw, e, q0);
+        walls.get(e, bw);
+        board_t wb;
+        if constexpr (BT::WIDE) wb = (uint64_t)bw[0] | ((uint64_t)bw[1] << 32);
+        else wb = bw[0];
+#pragma unroll
+        for (uint32_t d = 0; d < 4; ++d) {
+            uint32_t q[PR];
+#pragma unroll
+            for (int w = 0; w < PR; ++w) q[w] = q0[w];
+            slide_env<S, T>(q, wb, d);
+            bool moved = false;
+#pragma unroll
+            for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
+            mask4 |= (moved ? 1u : 0u) << (8 * e + d);
+        }
+    }
+    __stcs(reinterpret_cast<unsigned int*>(a.d_mask + e0), mask4);
+}
+
+template <int S, int T>
+inline cudaError_t launch_valid(const ts_valid_args& a, cudaStream_t stream) {
+    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
+    const unsigned blocks = (unsigned)((n_groups + 255) / 256);
+    if (blocks == 0) return cudaSuccess;
+    valid_kernel<S, T><<<blocks, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- standalone goal check (GameState.is_won, state.py:172-186) -------------------------------
+template <int S, int T>
+__global__ void __launch_bounds__(256) goal_kernel(const __grid_constant__ ts_goal_args a) {
+    using BT = BoardTraits<S>;
+    using board_t = typename BT::board_t;
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S), NWORDS = (NB + 3) / 4;
+    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
+    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_groups) return;
+    g += (size_t)a.first_env / GROUP;
+    const size_t e0 = g * GROUP;
+    uint32_t praw[PW];
+    ld_words<PW>(a.d_pos + e0 * PW, praw);
+    uint32_t won4 = 0;
+    if (a.goal_mode == TS_GOAL_ORDERED) {
+        uint32_t traw[PW];
+        ld_words<PW>(a.d_targets_packed + e0 * PW, traw);
+#pragma unroll
+        for (int e = 0; e < GROUP; ++e) {
+            uint32_t q[PR], t[PR];
+            group_elem<PW>(praw, e, q);
+            group_elem<PW>(traw, e, t);
+            bool won = true;
+#pragma unroll
+            for (int w = 0; w < PR; ++w) won &= q[w] == t[w];
+            won4 |= (won ? 1u : 0u) << (8 * e);
+        }
+    } else {
+        BoardGroup<NB> tboard;
+        tboard.load(a.d_targets_packed, (size_t)a.capacity, g);
+#pragma unroll
+        for (int e = 0; e < GROUP; ++e) {
+            uint32_t q[PR], tw[NWORDS];
+            group_elem<PW>(praw, e, q);
+            tboard.get(e, tw);
+            board_t tb;
+            if constexpr (BT::WIDE) tb = (uint64_t)tw[0] | ((uint64_t)tw[1] << 32);
+            else tb = tw[0];
+            won4 |= (occupancy<S, T>(q) == tb ? 1u : 0u) << (8 * e);
+        }
+    }
+    if (a.never_win) won4 = 0;
+    __stcs(reinterpret_cast<unsigned int*>(a.d_won + e0), won4);
+}
+
+template <int S, int T>
+inline cudaError_t launch_goal(const ts_goal_args& a, cudaStream_t stream) {
+    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
+    const unsigned blocks = (unsigned)((n_groups + 255) / 256);
+    if (blocks == 0) return cudaSuccess;
+    goal_kernel<S, T><<<blocks, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ts
