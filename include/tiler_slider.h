@@ -22,12 +22,16 @@
  *
  * Packed layout (struct-of-arrays, environment index innermost):
  *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.
- *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = (row<<4)|col of tile
- *    i, unused bytes zero.  Arrays: pos (in/out), init, targets (ordered mode).
- *  - board: bitboard of ts_board_bytes(S) = ceil(S*S/8) bytes per env, bit r*S+c set =
- *    blocked (walls) or target cell (targets, set mode), little endian, split into byte
- *    planes of width 16 (repeated), 8, 4, 2, 1 -- widest first; plane k of a buffer starts at
- *    byte offset ts_plane_offset(nb,k)*capacity and holds one element per env.
+ *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = row*PS + col of tile
+ *    i (PS = ts_pos_stride(S)), unused bytes zero.  Arrays: pos (in/out), init, targets
+ *    (ordered mode).
+ *  - board: bitboard of ts_board_bytes(S) bytes per env, bit row*BS + col (BS =
+ *    ts_board_stride(S)) set = blocked (walls) or target cell (targets, set mode), little
+ *    endian, split into byte planes of width 16 (repeated), 8, 4, 2, 1 -- widest first; plane
+ *    k of a buffer starts at byte offset ts_plane_offset(nb,k)*capacity and holds one element
+ *    per env.  S <= 6: BS = PS = S+1 and a WALL board also has column S of every row and all
+ *    bits past the last row set (sentinels that end a slide; ts_encode / ts_synth write
+ *    them).  S >= 7: BS = S, PS = 16, no sentinels.
  *  - step_count: uint8 per env when max_steps <= 255 (count_bytes = 1), else int32
  *    (count_bytes = 4).
  *  - actions: uint8 per env, 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (state.py:31-34).
@@ -76,6 +80,8 @@ const char *ts_last_error_string(void);
 /* layout queries (pure host arithmetic) */
 int ts_pos_bytes(int n_tiles);
 int ts_board_bytes(int size);
+int ts_board_stride(int size);   /* BS: bit index of cell (r,c) in a board = r*BS + c */
+int ts_pos_stride(int size);     /* PS: position byte of a tile at (r,c) = r*PS + c */
 int ts_plane_count(int n_bytes);
 int ts_plane_width(int n_bytes, int k);
 int ts_plane_offset(int n_bytes, int k);

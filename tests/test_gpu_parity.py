@@ -203,13 +203,13 @@ def test_synth_well_formed_and_shard_invariant(ts):
 def test_synthetic_rollout_vs_oracle(ts):
     """The bench workload itself: device-generated puzzles decoded to the host and replayed by
     the oracle (config 2 and config 3 shapes)."""
-    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True)]:
+    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False)]:
         N, K = 8192, 128
         env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, seed=1002, max_steps=100, auto_reset=True,
                                                  track_terminal=True)
         blocked = env.blocked_cells().cpu().numpy().astype(np.uint8)
         tiles = env.positions().cpu().numpy()
-        if multi:
+        if env.goal_mode == ts.GOAL_ORDERED:
             targets = env.target_positions().cpu().numpy()
         else:
             tgt_cells = env.target_positions().cpu().numpy()

@@ -35,7 +35,9 @@ def test_layout_arithmetic():
     from tiler_slider_b200 import _lib
     lib = _lib.lib()
     assert [lib.ts_pos_bytes(t) for t in range(1, 9)] == [1, 2, 4, 4, 8, 8, 8, 8]
-    assert [lib.ts_board_bytes(s) for s in (1, 4, 5, 6, 8, 12, 16)] == [1, 2, 4, 5, 8, 18, 32]
+    assert [lib.ts_board_bytes(s) for s in (1, 2, 3, 4, 5, 6, 7, 8, 12, 16)] == [1, 1, 2, 3, 4, 6, 7, 8, 18, 32]
+    assert [lib.ts_board_stride(s) for s in (1, 5, 6, 7, 8)] == [2, 6, 7, 7, 8]
+    assert [lib.ts_pos_stride(s) for s in (1, 5, 6, 7, 8, 12)] == [2, 6, 7, 16, 16, 16]
     for nb in range(1, 33):
         widths = [lib.ts_plane_width(nb, k) for k in range(lib.ts_plane_count(nb))]
         assert sum(widths) == nb and widths == sorted(widths, reverse=True)

@@ -6,7 +6,7 @@ max_steps), PyTorch tensors as containers, every computation done by the sm_100a
 libtiler_slider.so through the C-ABI (include/tiler_slider.h).  No CPU fallback.
 
 Packed state (see include/tiler_slider.h): `pos` is uint8[N, pos_bytes(T)], byte i of a row
-= (row<<4)|col of tile i.  `positions()` decodes to uint8[N, T, 2].
+= row*pos_stride + col of tile i.  `positions()` decodes to uint8[N, T, 2].
 """
 from __future__ import annotations
 
@@ -68,6 +68,8 @@ class BatchedTilerSliderEnv:
         self.capacity = _round_up(self.n_envs, CAP_ALIGN)
         self.pos_bytes = self._lib.ts_pos_bytes(self.n_tiles)
         self.board_bytes = self._lib.ts_board_bytes(self.size)
+        self.board_stride = self._lib.ts_board_stride(self.size)
+        self.pos_stride = self._lib.ts_pos_stride(self.size)
         self.count_bytes = 1 if self.max_steps <= 255 else 4
         cap, dev = self.capacity, self.device
         u8 = torch.uint8
@@ -85,6 +87,8 @@ class BatchedTilerSliderEnv:
         self._scratch_count = None
         self._scratch_flags = None
         self._host_ctx = None
+        self._cached_args = None
+        self._cached_out = None
         self._loaded = False
 
     # ------------------------------------------------------------------ construction
@@ -207,11 +211,16 @@ class BatchedTilerSliderEnv:
         holds is_won / invalid_move / timeout; with auto_reset the state of a finished env is
         already its reset state (its last positions are in `terminal_pos` if tracked)."""
         self._require_loaded()
-        a = self._step_args(self._stage_actions(actions))
+        ptr = self._stage_actions(actions)
+        a = self._cached_args
+        if a is None:
+            a = self._cached_args = self._step_args(ptr)
+            n = self.n_envs
+            self._cached_out = (self._pos[:n], self._reward[:n], self._done[:n].view(torch.bool))
+        a.d_actions = ptr
         with torch.cuda.device(self.device):
             check(self._lib.ts_step(C.byref(a), self._stream()), "ts_step")
-        n = self.n_envs
-        return self._pos[:n], self._reward[:n], self._done[:n].view(torch.bool)
+        return self._cached_out
 
     def raw_move(self, actions) -> torch.Tensor:
         """GameState.move (state.py:120-170) without episode bookkeeping: slides the tiles and
@@ -309,7 +318,8 @@ class BatchedTilerSliderEnv:
         """Decode packed position words to uint8[N, T, 2] (row, col)."""
         p = self.pos if packed is None else packed
         p = p[:, : self.n_tiles]
-        return torch.stack((p >> 4, p & 15), dim=-1)
+        ps = self.pos_stride
+        return torch.stack((p // ps, p % ps), dim=-1)
 
     def _board_cells(self, buf: torch.Tensor) -> torch.Tensor:
         """Unpack a plane-layout bitboard buffer to bool[N, S*S] (load-time / debugging aid)."""
@@ -320,7 +330,8 @@ class BatchedTilerSliderEnv:
             cols.append(buf[off * cap: (off + w) * cap].view(cap, w)[:n])
         by = torch.cat(cols, dim=1)                                          # [N, nb] bytes, little endian
         bits = (by.unsqueeze(-1) >> torch.arange(8, device=by.device, dtype=torch.uint8)) & 1
-        return bits.reshape(n, nb * 8)[:, : self.size * self.size].bool()
+        S, bs = self.size, self.board_stride
+        return bits.reshape(n, nb * 8)[:, : S * bs].reshape(n, S, bs)[:, :, :S].reshape(n, S * S).bool()
 
     def blocked_cells(self) -> torch.Tensor:
         return self._board_cells(self._walls)
@@ -329,7 +340,7 @@ class BatchedTilerSliderEnv:
         """Ordered mode: uint8[N,T,2].  Set mode: bool[N,S*S] target cells."""
         if self.goal_mode == GOAL_ORDERED:
             t = self._targets.view(self.capacity, self.pos_bytes)[: self.n_envs, : self.n_tiles]
-            return torch.stack((t >> 4, t & 15), dim=-1)
+            return torch.stack((t // self.pos_stride, t % self.pos_stride), dim=-1)
         return self._board_cells(self._targets)
 
     def observe(self, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -361,7 +372,7 @@ class BatchedTilerSliderEnv:
         """Overwrite current positions from uint8[N,T,2] (row, col) -- e.g. to expand a search
         frontier; validity is the caller's responsibility."""
         t = torch.as_tensor(tiles, dtype=torch.uint8).to(self.device)
-        packed = (t[..., 0] << 4) | (t[..., 1] & 15)
+        packed = t[..., 0] * self.pos_stride + t[..., 1]
         self._pos[: self.n_envs, : self.n_tiles] = packed
 
     def puzzle(self, i: int) -> Puzzle:
@@ -369,7 +380,7 @@ class BatchedTilerSliderEnv:
         S = self.size
         blocked = [(int(c) // S, int(c) % S) for c in torch.nonzero(self.blocked_cells()[i]).flatten().tolist()]
         init = self._init[i, : self.n_tiles].cpu()
-        tiles = [(int(b) >> 4, int(b) & 15) for b in init.tolist()]
+        tiles = [divmod(int(b), self.pos_stride) for b in init.tolist()]
         if self.goal_mode == GOAL_ORDERED:
             tg = [(int(r), int(c)) for r, c in self.target_positions()[i].cpu().tolist()]
         else:

@@ -59,37 +59,45 @@ __device__ __forceinline__ bool board_bit(const uint8_t* base, int nb, size_t ca
     return (base[board_byte_addr(nb, cap, env, bit >> 3)] >> (bit & 7)) & 1;
 }
 
+// value of bit `bit` of a stored WALL board: blocked cells, plus (padded boards) the sentinel
+// column S of every row and every bit past the last row
+__device__ __forceinline__ int wall_bit(const uint8_t* blocked_cells, int S, int bit) {
+    const int bs = board_stride(S);
+    const int r = bit / bs, c = bit % bs;
+    if (r >= S) return padded_board(S) ? 1 : 0;
+    if (c >= S) return 1;
+    return blocked_cells[r * S + c] ? 1 : 0;
+}
+
 // ---- K1 encode --------------------------------------------------------------------------------
 __global__ void encode_kernel(const ts_encode_args a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_envs) return;
     const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
     const int S = a.size, T = a.n_tiles, NT = a.n_targets, nb = board_bytes(S), pw = pos_bytes(T);
+    const int bs = board_stride(S), ps = pos_stride(S);
     const uint8_t* blk = a.d_blocked + (size_t)i * S * S;
     for (int b = 0; b < nb; ++b) {
         uint32_t v = 0;
-        for (int k = 0; k < 8; ++k) {
-            const int cell = 8 * b + k;
-            if (cell < S * S && blk[cell]) v |= 1u << k;
-        }
+        for (int k = 0; k < 8; ++k) v |= (uint32_t)wall_bit(blk, S, 8 * b + k) << k;
         a.d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
     }
     const uint8_t* tl = a.d_tiles + (size_t)i * T * 2;
     for (int t = 0; t < pw; ++t) {
-        const uint8_t v = t < T ? (uint8_t)((tl[2 * t] << 4) | (tl[2 * t + 1] & 15)) : 0;
+        const uint8_t v = t < T ? (uint8_t)(tl[2 * t] * ps + tl[2 * t + 1]) : 0;
         a.d_init[env * pw + t] = v;
         a.d_pos[env * pw + t] = v;
     }
     const uint8_t* tg = a.d_targets + (size_t)i * NT * 2;
     if (a.goal_mode == TS_GOAL_ORDERED) {
         for (int t = 0; t < pw; ++t)
-            a.d_targets_packed[env * pw + t] = t < NT ? (uint8_t)((tg[2 * t] << 4) | (tg[2 * t + 1] & 15)) : 0;
+            a.d_targets_packed[env * pw + t] = t < NT ? (uint8_t)(tg[2 * t] * ps + tg[2 * t + 1]) : 0;
     } else {
         for (int b = 0; b < nb; ++b) {
             uint32_t v = 0;
             for (int t = 0; t < NT; ++t) {
-                const int cell = tg[2 * t] * S + tg[2 * t + 1];
-                if ((cell >> 3) == b) v |= 1u << (cell & 7);
+                const int bit = tg[2 * t] * bs + tg[2 * t + 1];
+                if ((bit >> 3) == b) v |= 1u << (bit & 7);
             }
             a.d_targets_packed[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
         }
@@ -121,24 +129,32 @@ __global__ void synth_kernel(const ts_synth_args a) {
         perm[d] = perm[j];
         perm[j] = t;
     }
-    uint8_t wbytes[MAX_SIZE * MAX_SIZE / 8], tbytes[MAX_SIZE * MAX_SIZE / 8];
-    for (int b = 0; b < nb; ++b) wbytes[b] = tbytes[b] = 0;
-    for (int d = 0; d < W; ++d) wbytes[perm[d] >> 3] |= (uint8_t)(1u << (perm[d] & 7));
+    const int bs = board_stride(S), ps = pos_stride(S);
+    uint8_t cellmap[MAX_SIZE * MAX_SIZE];
+    for (int c = 0; c < cells; ++c) cellmap[c] = 0;
+    for (int d = 0; d < W; ++d) cellmap[perm[d]] = 1;
+    uint8_t tbytes[MAX_SIZE * MAX_SIZE / 8 + 8];
+    for (int b = 0; b < nb; ++b) {
+        uint32_t v = 0;
+        for (int k = 0; k < 8; ++k) v |= (uint32_t)wall_bit(cellmap, S, 8 * b + k) << k;
+        a.d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
+        tbytes[b] = 0;
+    }
     for (int t = 0; t < T; ++t) {
         const int c = perm[W + T + t];
-        tbytes[c >> 3] |= (uint8_t)(1u << (c & 7));
+        const int bit = (c / S) * bs + (c % S);
+        tbytes[bit >> 3] |= (uint8_t)(1u << (bit & 7));
     }
-    for (int b = 0; b < nb; ++b) a.d_walls[board_byte_addr(nb, cap, env, b)] = wbytes[b];
     for (int t = 0; t < pw; ++t) {
         uint8_t v = 0;
-        if (t < T) { const int c = perm[W + t]; v = (uint8_t)(((c / S) << 4) | (c % S)); }
+        if (t < T) { const int c = perm[W + t]; v = (uint8_t)((c / S) * ps + (c % S)); }
         a.d_init[env * pw + t] = v;
         a.d_pos[env * pw + t] = v;
     }
     if (a.goal_mode == TS_GOAL_ORDERED) {
         for (int t = 0; t < pw; ++t) {
             uint8_t v = 0;
-            if (t < T) { const int c = perm[W + T + t]; v = (uint8_t)(((c / S) << 4) | (c % S)); }
+            if (t < T) { const int c = perm[W + T + t]; v = (uint8_t)((c / S) * ps + (c % S)); }
             a.d_targets_packed[env * pw + t] = v;
         }
     } else {
@@ -155,8 +171,9 @@ __global__ void observe_kernel(const ts_observe_args a) {
     const int64_t i = idx / cells;
     const int cell = (int)(idx - i * cells);
     const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
-    const uint8_t rc = (uint8_t)(((cell / S) << 4) | (cell % S));
-    const float ch0 = board_bit(a.d_walls, nb, cap, env, cell) ? 1.0f : 0.0f;
+    const int bit = (cell / S) * board_stride(S) + (cell % S);
+    const uint8_t rc = (uint8_t)((cell / S) * pos_stride(S) + (cell % S));
+    const float ch0 = board_bit(a.d_walls, nb, cap, env, bit) ? 1.0f : 0.0f;
     float ch1 = 0.0f, ch2 = 0.0f;
     const bool ordered = a.goal_mode == TS_GOAL_ORDERED;
     for (int t = 0; t < T; ++t)
@@ -165,7 +182,7 @@ __global__ void observe_kernel(const ts_observe_args a) {
         for (int t = 0; t < T; ++t)
             if (a.d_targets_packed[env * pw + t] == rc) ch2 = (float)(t + 1);
     } else {
-        ch2 = board_bit(a.d_targets_packed, nb, cap, env, cell) ? 1.0f : 0.0f;
+        ch2 = board_bit(a.d_targets_packed, nb, cap, env, bit) ? 1.0f : 0.0f;
     }
     float* o = a.d_obs + (size_t)idx * 3;
     o[0] = ch0; o[1] = ch1; o[2] = ch2;
@@ -181,6 +198,8 @@ int ts_version(void) { return TS_VERSION; }
 const char* ts_last_error_string(void) { return g_err; }
 int ts_pos_bytes(int n_tiles) { return pos_bytes(n_tiles); }
 int ts_board_bytes(int size) { return board_bytes(size); }
+int ts_board_stride(int size) { return board_stride(size); }
+int ts_pos_stride(int size) { return pos_stride(size); }
 int ts_plane_count(int n_bytes) { return plane_count(n_bytes); }
 int ts_plane_width(int n_bytes, int k) { return plane_width(n_bytes, k); }
 int ts_plane_offset(int n_bytes, int k) { return plane_offset(n_bytes, k); }
@@ -230,17 +249,19 @@ int ts_step(const ts_step_args* a, void* stream) {
     for (const void* p : ptrs)
         if (p && !aligned16(p)) return fail(TS_E_MISALIGNED, "device pointer %p is not 16-byte aligned", p);
     if (a->n_envs == 0) return 0;
+    ts_step_args args = *a;
+    if (args.max_steps < 1) args.max_steps = 1;   // step_count >= max_steps holds on the first step either way
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
     switch (a->size) {
-        case 1: e = step_dispatch_s1(*a, st); break;
-        case 2: e = step_dispatch_s2(*a, st); break;
-        case 3: e = step_dispatch_s3(*a, st); break;
-        case 4: e = step_dispatch_s4(*a, st); break;
-        case 5: e = step_dispatch_s5(*a, st); break;
-        case 6: e = step_dispatch_s6(*a, st); break;
-        case 7: e = step_dispatch_s7(*a, st); break;
-        case 8: e = step_dispatch_s8(*a, st); break;
+        case 1: e = step_dispatch_s1(args, st); break;
+        case 2: e = step_dispatch_s2(args, st); break;
+        case 3: e = step_dispatch_s3(args, st); break;
+        case 4: e = step_dispatch_s4(args, st); break;
+        case 5: e = step_dispatch_s5(args, st); break;
+        case 6: e = step_dispatch_s6(args, st); break;
+        case 7: e = step_dispatch_s7(args, st); break;
+        case 8: e = step_dispatch_s8(args, st); break;
         default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
     }
     return cuda_result(e, "ts_step launch");

@@ -6,11 +6,17 @@
 //   explainrl/environment/state.py:172-186  GameState.is_won -> goal compare in the callers
 //
 // Layout in HBM (struct-of-arrays, environment index innermost):
-//   position word   one word of POS_BYTES(T) in {1,2,4,8} bytes per env; byte i = (row<<4)|col of
-//                   tile i, unused bytes are zero
-//   board planes    a bitboard of ceil(S*S/8) bytes per env, bit r*S+c, little endian, split
-//                   into byte planes of width 16/8/4/2/1 (widest first); plane k starts at byte
-//                   offset plane_offset(k)*capacity of the buffer and is indexed by env
+//   position word   one word of POS_BYTES(T) in {1,2,4,8} bytes per env; byte i = row*PS + col
+//                   of tile i with PS = pos_stride(S); unused bytes are zero
+//   board planes    a bitboard per env, bit row*BS + col with BS = board_stride(S), little
+//                   endian, board_bytes(S) bytes, split into byte planes of width 16/8/4/2/1
+//                   (widest first); plane k starts at byte offset plane_offset(k)*capacity of
+//                   the buffer and is indexed by env
+//   S <= 6 ("padded" boards): BS = PS = S+1.  Column S of every row of a WALL board and all
+//                   bits past the last row are stored as 1 (sentinels): a slide toward higher
+//                   indices stops there without any per-tile edge test.  Target boards (set
+//                   goal) use the same stride without sentinels.
+//   S >= 7 (compact boards): BS = S, PS = 16, no sentinels.
 //   capacity        allocation stride in envs, a multiple of 128 so that every plane start and
 //                   every 4-env group is 16-byte aligned
 // A thread owns GROUP=4 consecutive envs, so every stream is read with one 32/64/128-bit
@@ -28,7 +34,11 @@ constexpr int MAX_SIZE = 16;
 constexpr int MAX_TILES = 8;
 
 __host__ __device__ constexpr int pos_bytes(int T) { return T <= 1 ? 1 : T <= 2 ? 2 : T <= 4 ? 4 : 8; }
-__host__ __device__ constexpr int board_bytes(int S) { return (S * S + 7) / 8; }
+__host__ __device__ constexpr bool padded_board(int S) { return S <= 6; }
+__host__ __device__ constexpr int board_stride(int S) { return padded_board(S) ? S + 1 : S; }
+__host__ __device__ constexpr int pos_stride(int S) { return padded_board(S) ? S + 1 : 16; }
+__host__ __device__ constexpr int board_bits(int S) { return S * board_stride(S); }
+__host__ __device__ constexpr int board_bytes(int S) { return (board_bits(S) + 7) / 8; }
 
 // decomposition of nb bytes into planes of width 16 (repeated), 8, 4, 2, 1
 __host__ __device__ constexpr int plane_count(int nb) {
@@ -182,51 +192,124 @@ template <int I> __device__ __forceinline__ uint32_t byte_of(uint32_t x) {
 //
 // Closed form (checked against the reference by the parity tests): inside every
 // maximal wall-free run of a line, tiles keep their order and pack against the run's end in
-// the move direction.  For a tile at offset o whose run ends before offset e (nearest wall
-// above o, or the edge), the new offset is  o + #empty cells in (o, e).
+// the move direction.  For a tile whose run ends before cell e (nearest wall past the tile,
+// or the edge), the new position is  old + (#empty cells strictly between the tile and e).
+// Every tile is independent of the others given the occupancy bitboard -- no ordering, no
+// back-off loop.
 //
-// The four directions share one code path: the board is rotated by 180 degrees for UP/LEFT
-// so that every move is "toward higher offsets", positions are nibble-swapped for vertical
-// moves so that (line, offset) = (col, row), and the wall bits of a vertical line are
-// gathered from the row-major bitboard with one multiply (bits S*k -> B+k, B=(S-1)^2; all
-// 36 partial products land on distinct bits, so there are no carries).
-// Bitboard variant: S*S <= 64.
+// The four directions share one code path: UP/LEFT rotate the board and the positions by 180
+// degrees so that every move goes "toward higher bit indices".
 // =============================================================================================
+
+// ---- padded boards (S <= 6): stride S+1, sentinel column + sentinel tail ---------------------
+// In bit-index space a horizontal move has stride 1 and a vertical move stride BS = S+1.  For
+// a tile at bit p the cells it can reach are bits p+st, p+2st, ... of (walls >> (p+st)),
+// restricted to the line mask LM (all bits for a row, bits 0,BS,2BS,... for a column).  The
+// sentinel column ends a row, the sentinel tail (all ones from bit S*BS-1 up) ends a column, so
+//     t1 = (walls >> sh) & LM            first set bit = first non-enterable cell
+//     run = (t1 - 1) & ~t1               cells before it
+//     n   = popc(run & LM & ~(occ >> sh))
+//     p  += st * n
+// is the whole per-tile computation: no gather, no transposition, no edge test.
+template <int S> struct Padded {
+    static constexpr int BS = S + 1;
+    static constexpr int NBITS = S * BS;                    // stored board bits incl. sentinel column
+    static constexpr int KREV = NBITS - 2;                  // 180-degree rotation: bit i <-> KREV - i
+    static constexpr uint32_t KREV4 = 0x01010101u * (uint32_t)KREV;
+    static constexpr uint64_t TAIL = ~0ull << (NBITS - 1);  // sentinel of the last row + everything above
+    static constexpr uint32_t col_mask() { uint32_t m = 0; for (int k = 0; k * BS < 32 && k < S; ++k) m |= 1u << (k * BS); return m; }
+    static constexpr uint32_t COL = col_mask();
+    static constexpr uint64_t sentinel_cols() { uint64_t m = 0; for (int r = 0; r < S; ++r) m |= 1ull << (r * BS + S); return m; }
+    static constexpr uint64_t SENT = sentinel_cols() | (~0ull << NBITS);   // what a stored wall board has set
+};
+
+template <int S, int T>
+__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
+    using PD = Padded<S>;
+    constexpr int PR = (T + 3) / 4;
+    // Direction parameters as integer multiply-adds: the kernel is bound by the ALU pipe
+    // (LOP3/SHF/SEL/PRMT), so selects are moved to the FMA pipe (IMAD) wherever possible.
+    const uint32_t h = (action >> 1) & 1u;                 // 1 = LEFT/RIGHT
+    const uint32_t f = (action & 1u) ^ 1u;                 // 1 = UP/LEFT: rotate by 180 degrees
+    const uint32_t st = (uint32_t)PD::BS - h * (uint32_t)(PD::BS - 1);   // h ? 1 : BS
+    const uint32_t lm = PD::COL + h * ~PD::COL;                           // h ? ~0 : COL
+    const uint32_t fm = 1u - 2u * f;                                      // f ? -1 : +1
+    const uint32_t fk = f * PD::KREV4;                                    // f ? KREV4 : 0
+    // bytes past the stored board read as zero in the plane layout: (re)assert the sentinels
+    const uint64_t w0 = walls | (~0ull << PD::NBITS);
+    const uint64_t wr = (__brevll(walls) >> (63 - PD::KREV)) | PD::TAIL;
+    const uint64_t wb = f ? wr : w0;
+
+    uint32_t P[PR], ACC[PR], sh[T];
+    uint64_t occ = 0;
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        P[w] = q[w] * fm + fk;                             // f ? KREV4 - q : q (bytewise, no borrow)
+        ACC[w] = 0;
+    }
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t p = byte_of<i % 4>(P[i / 4]);
+        if constexpr (T > 1) occ |= 1ull << p;
+        sh[i] = p + st;
+    });
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t t1 = (uint32_t)(wb >> sh[i]) & lm;
+        const uint32_t t2 = t1 - 1u;
+        uint32_t empty;
+        if constexpr (T > 1) {
+            const uint32_t free_cells = ~(uint32_t)(occ >> sh[i]) & lm;
+            empty = t2 & ~t1 & free_cells;
+        } else {
+            empty = t2 & ~t1 & lm;
+        }
+        ACC[i / 4] = (uint32_t)__popc(empty) * (1u << (8 * (i % 4))) + ACC[i / 4];
+    });
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        const uint32_t pn = st * ACC[w] + P[w];
+        q[w] = pn * fm + fk;
+    }
+    // unused bytes of the last word stay zero: KREV4-(KREV4-0) = 0 and nothing is accumulated
+    // into them (the flipped value KREV of an unused byte is never read as a tile).
+}
+
+template <int S, int T>
+__device__ __forceinline__ uint64_t occupancy_padded(const uint32_t (&q)[(T + 3) / 4]) {
+    uint64_t occ = 0;
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        occ |= 1ull << byte_of<i % 4>(q[i / 4]);
+    });
+    return occ;
+}
+
+// ---- compact boards (S = 7, 8): stride S, position byte (row<<4)|col ---------------------------
+// Positions are nibble-swapped for vertical moves so that (line, offset) = (col, row); the wall
+// bits of a vertical line are gathered from the row-major bitboard with one multiply (bits
+// S*k -> GSHIFT+k; all partial products land on distinct bits, so there are no carries).
 __host__ __device__ constexpr uint64_t make_col0(int S) { uint64_t m = 0; for (int k = 0; k < S; ++k) m |= 1ull << (S * k); return m; }
 __host__ __device__ constexpr uint64_t make_magic(int S) { uint64_t m = 0; for (int j = 0; j < S; ++j) m |= 1ull << ((S - 1) * (S - 1) - (S - 1) * j); return m; }
 
-template <int S> struct BoardTraits {
-    static constexpr int NBITS = S * S;
-    static constexpr bool WIDE = NBITS > 32;                 // board needs 64 bits
-    static constexpr bool GATHER32 = S * (S - 1) <= 31;      // column gather fits a 32-bit multiply
-    using board_t = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
+template <int S> struct Compact {
     static constexpr uint64_t COL0 = make_col0(S);           // bits S*k, k < S: column 0
     static constexpr uint64_t MAGIC = make_magic(S);         // moves bit S*k to bit GSHIFT+k
     static constexpr int GSHIFT = (S - 1) * (S - 1);
 };
 
-template <int S> __device__ __forceinline__ typename BoardTraits<S>::board_t rot180(typename BoardTraits<S>::board_t w) {
-    if constexpr (BoardTraits<S>::WIDE) return __brevll(w) >> (64 - S * S);
-    else return __brev(w) >> (32 - S * S);
-}
-
-// q[PR]: packed position words ((row<<4)|col per byte).  Updated in place.  walls: row-major
-// bitboard.  action: 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (state.py:31-34).
 template <int S, int T>
-__device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], typename BoardTraits<S>::board_t walls, uint32_t action) {
-    using BT = BoardTraits<S>;
-    using board_t = typename BT::board_t;
+__device__ __forceinline__ void slide_compact(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
+    using CT = Compact<S>;
     constexpr int PR = (T + 3) / 4;
     constexpr uint32_t KFLIP = 0x11111111u * (uint32_t)(S - 1);
     const bool horiz = (action & 2u) != 0;
     const bool flip = (action & 1u) == 0;
-
-    const board_t wb = flip ? rot180<S>(walls) : walls;
-    // vertical: line = column -> read the column through the multiply gather
-    const uint32_t line_mul = horiz ? (uint32_t)S : 1u;
+    const uint64_t wb = flip ? (__brevll(walls) >> (64 - S * S)) : walls;
+    const uint32_t line_mul = horiz ? (uint32_t)S : 1u;   // vertical: shift by the column, then gather
 
     uint32_t Q[PR], LSo[PR], LSw[PR], OFF[PR];
-    board_t occ = 0;
+    uint64_t occ = 0;
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
         uint32_t x = horiz ? q[w] : swap_nibbles(q[w]);
@@ -239,53 +322,58 @@ __device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], typename B
     }
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        const uint32_t p = byte_of<i % 4>(LSo[i / 4] + OFF[i / 4]);
-        occ |= (board_t)1 << p;
+        occ |= 1ull << byte_of<i % 4>(LSo[i / 4] + OFF[i / 4]);
     });
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
         const uint32_t shw = byte_of<i % 4>(LSw[i / 4]);
         const uint32_t sho = byte_of<i % 4>(LSo[i / 4]);
         const uint32_t o = byte_of<i % 4>(OFF[i / 4]);
-        uint32_t wl;
-        if constexpr (BT::GATHER32) {
-            const uint32_t x = (uint32_t)(wb >> shw);
-            const uint32_t g = ((x & (uint32_t)BT::COL0) * (uint32_t)BT::MAGIC) >> BT::GSHIFT;
-            wl = horiz ? x : g;
-        } else {
-            const board_t x = wb >> shw;
-            const uint32_t g = (uint32_t)(((x & (board_t)BT::COL0) * (board_t)BT::MAGIC) >> BT::GSHIFT);
-            wl = horiz ? (uint32_t)x : g;
-        }
+        const uint64_t x = wb >> shw;
+        const uint32_t g = (uint32_t)(((x & CT::COL0) * CT::MAGIC) >> CT::GSHIFT);
+        const uint32_t wl = horiz ? (uint32_t)x : g;
         const uint32_t ol = (uint32_t)(occ >> sho);
         const uint32_t above = 0xFFFFFFFEu << o;           // offsets > o
         const uint32_t blk = (wl & above) | (1u << S);     // walls above o, edge sentinel at S
         const uint32_t run = (blk - 1u) & ~blk;            // offsets below the nearest wall
-        const uint32_t empty = run & above & ~ol;
-        Q[i / 4] += (uint32_t)__popc(empty) << (8 * (i % 4));
+        Q[i / 4] += (uint32_t)__popc(run & above & ~ol) << (8 * (i % 4));
     });
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
-        uint32_t x = flip ? KFLIP - Q[w] : Q[w];
+        const uint32_t x = flip ? KFLIP - Q[w] : Q[w];
         q[w] = horiz ? x : swap_nibbles(x);
     }
-    // unused bytes of the last word were zero and come back zero:
-    // KFLIP-(KFLIP-0)=0 and swap_nibbles(0)=0; no count was added to them.
 }
 
-// occupancy bitboard (bit r*S+c) of packed positions
 template <int S, int T>
-__device__ __forceinline__ typename BoardTraits<S>::board_t occupancy(const uint32_t (&q)[(T + 3) / 4]) {
-    using board_t = typename BoardTraits<S>::board_t;
-    board_t occ = 0;
+__device__ __forceinline__ uint64_t occupancy_compact(const uint32_t (&q)[(T + 3) / 4]) {
+    uint64_t occ = 0;
     uint32_t P[(T + 3) / 4];
 #pragma unroll
     for (int w = 0; w < (T + 3) / 4; ++w) P[w] = ((q[w] >> 4) & 0x0F0F0F0Fu) * (uint32_t)S + (q[w] & 0x0F0F0F0Fu);
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        occ |= (board_t)1 << byte_of<i % 4>(P[i / 4]);
+        occ |= 1ull << byte_of<i % 4>(P[i / 4]);
     });
     return occ;
+}
+
+// ---- dispatch by board class (S*BS <= 64 bits) ---------------------------------------------------
+// q[PR]: packed position words.  Updated in place.  action: 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT
+// (state.py:31-34).
+template <int S, int T>
+__device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
+    if constexpr (padded_board(S)) slide_padded<S, T>(q, walls, action);
+    else slide_compact<S, T>(q, walls, action);
+}
+template <int S, int T>
+__device__ __forceinline__ uint64_t occupancy(const uint32_t (&q)[(T + 3) / 4]) {
+    if constexpr (padded_board(S)) return occupancy_padded<S, T>(q);
+    else return occupancy_compact<S, T>(q);
+}
+template <int NWORDS> __device__ __forceinline__ uint64_t board64(const uint32_t (&bw)[NWORDS]) {
+    if constexpr (NWORDS >= 2) return (uint64_t)bw[0] | ((uint64_t)bw[1] << 32);
+    else return bw[0];
 }
 
 // flag bits (mirrored in include/tiler_slider.h)

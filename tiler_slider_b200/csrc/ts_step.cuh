@@ -1,4 +1,4 @@
-// ts_step.cuh -- K2, the fused step kernel (bitboard variant, S*S <= 64).
+// ts_step.cuh -- K2, the fused step kernel (bitboard variant, boards of at most 64 bits).
 //
 // One launch advances every env of the range by one externally supplied action and fuses
 //   GameState.move            explainrl/environment/state.py:120-170   (slide_env)
@@ -7,7 +7,8 @@
 //                             invalid_move, done, step counter, timeout
 //   TilerSliderEnv.reset      explainrl/environment/environment.py:89-97 (optional auto-reset)
 // plus the repo-defined reward.  Thread = 4 consecutive envs; all traffic is 32/64/128-bit
-// coalesced, algorithmic bytes per env-step are 3T + ceil(S^2/8) + 8.
+// coalesced.  The kernel is bound by the integer ALU pipe, not by HBM (profiles/), so the
+// per-env bookkeeping is done SWAR on the four packed status bytes of the thread's envs.
 #pragma once
 #include "ts_common.cuh"
 #include "../../include/tiler_slider.h"
@@ -16,10 +17,17 @@ namespace ts {
 
 constexpr int STEP_THREADS = 256;
 
-template <int S, int T, int GOAL>
+// bit 7 of every byte of the result = (byte of a) >= (byte of b); b given as its low 7 bits
+// (b_lo) and its bit 7 (b_hi), both replicated per byte
+__device__ __forceinline__ uint32_t swar_ge_u8(uint32_t a, uint32_t b_lo, uint32_t b_hi) {
+    const uint32_t t = (a | 0x80808080u) - b_lo;           // bit7: (a & 0x7f) >= (b & 0x7f); no cross-byte borrow
+    return ((a & ~b_hi) | (~(a ^ b_hi) & t)) & 0x80808080u;
+}
+
+// AR: auto-reset on (flags are write-only) / off (done envs are frozen and report STALE)
+// CW: bytes of the step counter (1: SWAR bookkeeping, 4: per-env)
+template <int S, int T, int GOAL, bool AR, int CW>
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constant__ ts_step_args a) {
-    using BT = BoardTraits<S>;
-    using board_t = typename BT::board_t;
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S);
     constexpr int NWORDS = (NB + 3) / 4;
 
@@ -40,23 +48,23 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     if constexpr (GOAL == TS_GOAL_ORDERED) ld_words<PW>(a.d_targets_packed + e0 * PW, traw);
     else tboard.load(a.d_targets_packed, cap, g);
     const uint32_t act4 = __ldcs(reinterpret_cast<const unsigned int*>(a.d_actions + e0));
-    const bool wide_count = a.count_bytes == 4;
-    uint32_t cnt[GROUP];
-    if (wide_count) {
-        const uint4 c = __ldcs(reinterpret_cast<const uint4*>(a.d_step_count) + g);
-        cnt[0] = c.x; cnt[1] = c.y; cnt[2] = c.z; cnt[3] = c.w;
+    uint32_t cnt4 = 0, cntw[GROUP];
+    if constexpr (CW == 1) {
+        cnt4 = __ldcs(reinterpret_cast<const unsigned int*>(a.d_step_count) + g);
     } else {
-        const uint32_t c = __ldcs(reinterpret_cast<const unsigned int*>(a.d_step_count) + g);
-        cnt[0] = c & 0xFF; cnt[1] = (c >> 8) & 0xFF; cnt[2] = (c >> 16) & 0xFF; cnt[3] = c >> 24;
+        const uint4 c = __ldcs(reinterpret_cast<const uint4*>(a.d_step_count) + g);
+        cntw[0] = c.x; cntw[1] = c.y; cntw[2] = c.z; cntw[3] = c.w;
     }
     uint32_t prev_flags = 0;
-    if (!a.auto_reset) prev_flags = __ldcs(reinterpret_cast<const unsigned int*>(a.d_flags + e0));
+    if constexpr (!AR) prev_flags = __ldcs(reinterpret_cast<const unsigned int*>(a.d_flags + e0));
 
     uint32_t pnew[PW];
 #pragma unroll
     for (int j = 0; j < PW; ++j) pnew[j] = praw[j];
-    uint32_t flags4 = 0, done4 = 0;
+    uint32_t wm4 = 0;        // per byte: F_WON | F_INVALID of this step
+    uint32_t to7 = 0;        // per byte: bit 7 = timeout (CW == 4 path fills it per env)
     float rew[GROUP];
+    const bool can_win = a.never_win == 0;
 
 #pragma unroll
     for (int e = 0; e < GROUP; ++e) {
@@ -65,78 +73,100 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
         walls.get(e, bw);
-        board_t wb;
-        if constexpr (BT::WIDE) wb = (uint64_t)bw[0] | ((uint64_t)bw[1] << 32);
-        else wb = bw[0];
         const uint32_t action = (act4 >> (8 * e)) & 3u;
 
-        slide_env<S, T>(q, wb, action);
+        slide_env<S, T>(q, board64(bw), action);
 
         bool moved = false;
 #pragma unroll
         for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
-        bool won;
+        bool won = can_win;
         if constexpr (GOAL == TS_GOAL_ORDERED) {
             uint32_t tq[PR];
             group_elem<PW>(traw, e, tq);
-            won = true;
 #pragma unroll
             for (int w = 0; w < PR; ++w) won &= q[w] == tq[w];
         } else {
             uint32_t tw[NWORDS];
             tboard.get(e, tw);
-            board_t tb;
-            if constexpr (BT::WIDE) tb = (uint64_t)tw[0] | ((uint64_t)tw[1] << 32);
-            else tb = tw[0];
-            won = occupancy<S, T>(q) == tb;
+            won &= occupancy<S, T>(q) == board64(tw);
         }
-        won = won && !a.never_win;
-        const uint32_t c1 = cnt[e] + 1u;
-        const bool timeout = (int)c1 >= a.max_steps;
-        const bool done = won || timeout;
-        uint32_t f = (done ? F_DONE : 0u) | (won ? F_WON : 0u) | (moved ? 0u : F_INVALID) | (timeout ? F_TIMEOUT : 0u);
-        float r = won ? a.r_win : (moved ? a.r_step : a.r_invalid);
-        uint32_t cn = c1;
-        const bool stale = ((prev_flags >> (8 * e)) & F_DONE) != 0;   // only ever set when !auto_reset
-        if (stale) {
-            f = F_DONE | F_STALE;
-            r = 0.0f;
-            cn = cnt[e];
-#pragma unroll
-            for (int w = 0; w < PR; ++w) q[w] = q0[w];
+        rew[e] = won ? a.r_win : (moved ? a.r_step : a.r_invalid);
+        uint32_t wm = won ? F_WON : 0u;
+        if (!moved) wm |= F_INVALID;
+        wm4 = wm * (1u << (8 * e)) + wm4;
+        if constexpr (CW == 4) {
+            cntw[e] += 1u;
+            if ((int)cntw[e] >= a.max_steps) to7 |= 0x80u << (8 * e);
         }
-        cnt[e] = cn;
-        rew[e] = r;
-        flags4 |= f << (8 * e);
-        done4 |= (f & F_DONE) << (8 * e);
         group_set<PW>(pnew, e, q);
     }
 
-    // ---- auto-reset (environment.py:89-97) and the optional terminal snapshot ----------------
-    if (done4 != 0 && a.auto_reset) {
-        if (a.d_terminal_pos) st_words<PW>(a.d_terminal_pos + e0 * PW, pnew);
-        uint32_t iraw[PW];
-        ld_words<PW>(a.d_init + e0 * PW, iraw);
+    // ---- SWAR bookkeeping on the four status bytes (environment.py:133-141) -------------------
+    uint32_t c1 = 0;
+    if constexpr (CW == 1) {
+        c1 = cnt4 + 0x01010101u;                              // step_count += 1 (never wraps: count < max_steps <= 255)
+        const uint32_t ms = (uint32_t)a.max_steps;
+        to7 = swar_ge_u8(c1, (ms & 0x7Fu) * 0x01010101u, (ms & 0x80u) * 0x01010101u);
+    }
+    uint32_t done1 = ((wm4 >> 1) | (to7 >> 7)) & 0x01010101u;     // won or timeout
+    uint32_t flags4 = wm4 | (to7 >> 4) | done1;
+    if constexpr (!AR) {
+        // envs that were already done are frozen: positions, counter and status untouched
+        const uint32_t stale1 = prev_flags & 0x01010101u;
+        if (stale1) {
+            const uint32_t sm = stale1 * 0xFFu;
+            flags4 = (flags4 & ~sm) | (stale1 * (F_DONE | F_STALE));
+            done1 |= stale1;
+            c1 = (c1 & ~sm) | (cnt4 & sm);
 #pragma unroll
-        for (int e = 0; e < GROUP; ++e) {
-            if ((done4 >> (8 * e)) & 1u) {
-                uint32_t q[PR];
-                group_elem<PW>(iraw, e, q);
-                group_set<PW>(pnew, e, q);
-                cnt[e] = 0;
+            for (int e = 0; e < GROUP; ++e) {
+                if ((stale1 >> (8 * e)) & 1u) {
+                    uint32_t q0[PR];
+                    group_elem<PW>(praw, e, q0);
+                    group_set<PW>(pnew, e, q0);
+                    rew[e] = 0.0f;
+                    if constexpr (CW == 4) cntw[e] -= 1u;
+                }
             }
         }
-    } else if (done4 != 0 && a.d_terminal_pos) {
-        st_words<PW>(a.d_terminal_pos + e0 * PW, pnew);
+    }
+
+    // ---- auto-reset (environment.py:89-97) and the optional terminal snapshot ----------------
+    if (done1 != 0) {
+        if (a.d_terminal_pos) st_words<PW>(a.d_terminal_pos + e0 * PW, pnew);
+        if constexpr (AR) {
+            uint32_t iraw[PW];
+            ld_words<PW>(a.d_init + e0 * PW, iraw);
+            c1 &= ~(done1 * 0xFFu);
+#pragma unroll
+            for (int e = 0; e < GROUP; ++e) {
+                if ((done1 >> (8 * e)) & 1u) {
+                    uint32_t q[PR];
+                    group_elem<PW>(iraw, e, q);
+                    group_set<PW>(pnew, e, q);
+                    if constexpr (CW == 4) cntw[e] = 0;
+                }
+            }
+        }
     }
 
     // ---- stores --------------------------------------------------------------------------------
     st_words<PW>(a.d_pos + e0 * PW, pnew);
-    if (wide_count) __stcs(reinterpret_cast<uint4*>(a.d_step_count) + g, make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]));
-    else __stcs(reinterpret_cast<unsigned int*>(a.d_step_count) + g, cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24));
+    if constexpr (CW == 1) __stcs(reinterpret_cast<unsigned int*>(a.d_step_count) + g, c1);
+    else __stcs(reinterpret_cast<uint4*>(a.d_step_count) + g, make_uint4(cntw[0], cntw[1], cntw[2], cntw[3]));
     __stcs(reinterpret_cast<float4*>(a.d_reward) + g, make_float4(rew[0], rew[1], rew[2], rew[3]));
-    if (a.d_done) __stcs(reinterpret_cast<unsigned int*>(a.d_done + e0), done4);
+    if (a.d_done) __stcs(reinterpret_cast<unsigned int*>(a.d_done + e0), done1);
     if (a.d_flags) __stcs(reinterpret_cast<unsigned int*>(a.d_flags + e0), flags4);
+}
+
+template <int S, int T, int GOAL>
+inline void launch_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t stream) {
+    const bool ar = a.auto_reset != 0, narrow = a.count_bytes == 1;
+    if (ar && narrow) step_kernel<S, T, GOAL, true, 1><<<blocks, STEP_THREADS, 0, stream>>>(a);
+    else if (ar) step_kernel<S, T, GOAL, true, 4><<<blocks, STEP_THREADS, 0, stream>>>(a);
+    else if (narrow) step_kernel<S, T, GOAL, false, 1><<<blocks, STEP_THREADS, 0, stream>>>(a);
+    else step_kernel<S, T, GOAL, false, 4><<<blocks, STEP_THREADS, 0, stream>>>(a);
 }
 
 template <int S, int T>
@@ -144,8 +174,8 @@ inline cudaError_t launch_step(const ts_step_args& a, cudaStream_t stream) {
     const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
     const unsigned blocks = (unsigned)((n_groups + STEP_THREADS - 1) / STEP_THREADS);
     if (blocks == 0) return cudaSuccess;
-    if (a.goal_mode == TS_GOAL_ORDERED) step_kernel<S, T, TS_GOAL_ORDERED><<<blocks, STEP_THREADS, 0, stream>>>(a);
-    else step_kernel<S, T, TS_GOAL_SET><<<blocks, STEP_THREADS, 0, stream>>>(a);
+    if (a.goal_mode == TS_GOAL_ORDERED) launch_step_goal<S, T, TS_GOAL_ORDERED>(a, blocks, stream);
+    else launch_step_goal<S, T, TS_GOAL_SET>(a, blocks, stream);
     return cudaGetLastError();
 }
 

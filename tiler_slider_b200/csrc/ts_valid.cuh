@@ -9,8 +9,6 @@ namespace ts {
 
 template <int S, int T>
 __global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_valid_args a) {
-    using BT = BoardTraits<S>;
-    using board_t = typename BT::board_t;
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S), NWORDS = (NB + 3) / 4;
     const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
     size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -27,9 +25,7 @@ __global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_v
         uint32_t q0[PR], bw[NWORDS];
         group_elem<PW>(praw, e, q0);
         walls.get(e, bw);
-        board_t wb;
-        if constexpr (BT::WIDE) wb = (uint64_t)bw[0] | ((uint64_t)bw[1] << 32);
-        else wb = bw[0];
+        const uint64_t wb = board64(bw);
 #pragma unroll
         for (uint32_t d = 0; d < 4; ++d) {
             uint32_t q[PR];
@@ -57,8 +53,6 @@ inline cudaError_t launch_valid(const ts_valid_args& a, cudaStream_t stream) {
 // ---- standalone goal check (GameState.is_won, state.py:172-186) -------------------------------
 template <int S, int T>
 __global__ void __launch_bounds__(256) goal_kernel(const __grid_constant__ ts_goal_args a) {
-    using BT = BoardTraits<S>;
-    using board_t = typename BT::board_t;
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S), NWORDS = (NB + 3) / 4;
     const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
     size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -89,9 +83,7 @@ __global__ void __launch_bounds__(256) goal_kernel(const __grid_constant__ ts_go
             uint32_t q[PR], tw[NWORDS];
             group_elem<PW>(praw, e, q);
             tboard.get(e, tw);
-            board_t tb;
-            if constexpr (BT::WIDE) tb = (uint64_t)tw[0] | ((uint64_t)tw[1] << 32);
-            else tb = tw[0];
+            const uint64_t tb = board64(tw);
             won4 |= (occupancy<S, T>(q) == tb ? 1u : 0u) << (8 * e);
         }
     }
