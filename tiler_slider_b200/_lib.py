@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtiler_slider.so")
+# TS_LIB_PATH: load another build of the same library (kernel experiments only)
+LIB_PATH = os.environ.get("TS_LIB_PATH") or os.path.join(_HERE, "libtiler_slider.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 CAP_ALIGN = 128

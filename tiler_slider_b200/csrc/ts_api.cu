@@ -37,6 +37,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 static int check_shape(int size, int n_tiles, int64_t first, int64_t n, int64_t cap) {
     if (size < 1 || size > MAX_SIZE) return fail(TS_E_BAD_SIZE, "size %d outside 1..%d", size, MAX_SIZE);
     if (n_tiles < 1 || n_tiles > MAX_TILES) return fail(TS_E_BAD_TILES, "n_tiles %d outside 1..%d", n_tiles, MAX_TILES);
+    if (cap >= (int64_t)1 << 33) return fail(TS_E_BAD_CAPACITY, "capacity %lld too large (max 2^33 - 128 envs per call)", (long long)cap);
     if (cap <= 0 || cap % CAP_ALIGN != 0) return fail(TS_E_BAD_CAPACITY, "capacity %lld is not a positive multiple of %d", (long long)cap, CAP_ALIGN);
     if (first < 0 || n < 0 || first % GROUP != 0 || first + n > cap)
         return fail(TS_E_BAD_RANGE, "env range [%lld, %lld) invalid for capacity %lld (first_env must be a multiple of %d)",

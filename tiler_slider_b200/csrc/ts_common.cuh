@@ -179,6 +179,13 @@ template <int NB> struct BoardGroup {
     }
 };
 
+// integer multiply-add pinned to the FMA pipe (IMAD), keeping it off the saturated ALU pipe
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // ---- SWAR helpers on 4 packed position bytes -------------------------------------------------
 __device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {
     return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
@@ -223,14 +230,13 @@ template <int S> struct Padded {
     static constexpr uint64_t SENT = sentinel_cols() | (~0ull << NBITS);   // what a stored wall board has set
 };
 
+// h = 1 for LEFT/RIGHT, f = 1 for UP/LEFT (the directions that need the 180-degree rotation)
 template <int S, int T>
-__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
+__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t h, uint32_t f) {
     using PD = Padded<S>;
     constexpr int PR = (T + 3) / 4;
     // Direction parameters as integer multiply-adds: the kernel is bound by the ALU pipe
     // (LOP3/SHF/SEL/PRMT), so selects are moved to the FMA pipe (IMAD) wherever possible.
-    const uint32_t h = (action >> 1) & 1u;                 // 1 = LEFT/RIGHT
-    const uint32_t f = (action & 1u) ^ 1u;                 // 1 = UP/LEFT: rotate by 180 degrees
     const uint32_t st = (uint32_t)PD::BS - h * (uint32_t)(PD::BS - 1);   // h ? 1 : BS
     const uint32_t lm = PD::COL + h * ~PD::COL;                           // h ? ~0 : COL
     const uint32_t fm = 1u - 2u * f;                                      // f ? -1 : +1
@@ -264,7 +270,7 @@ __device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_
         } else {
             empty = t2 & ~t1 & lm;
         }
-        ACC[i / 4] = (uint32_t)__popc(empty) * (1u << (8 * (i % 4))) + ACC[i / 4];
+        ACC[i / 4] = mad_u32((uint32_t)__popc(empty), 1u << (8 * (i % 4)), ACC[i / 4]);
     });
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
@@ -299,12 +305,12 @@ template <int S> struct Compact {
 };
 
 template <int S, int T>
-__device__ __forceinline__ void slide_compact(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
+__device__ __forceinline__ void slide_compact(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t h, uint32_t f) {
     using CT = Compact<S>;
     constexpr int PR = (T + 3) / 4;
     constexpr uint32_t KFLIP = 0x11111111u * (uint32_t)(S - 1);
-    const bool horiz = (action & 2u) != 0;
-    const bool flip = (action & 1u) == 0;
+    const bool horiz = h != 0;
+    const bool flip = f != 0;
     const uint64_t wb = flip ? (__brevll(walls) >> (64 - S * S)) : walls;
     const uint32_t line_mul = horiz ? (uint32_t)S : 1u;   // vertical: shift by the column, then gather
 
@@ -362,10 +368,13 @@ __device__ __forceinline__ uint64_t occupancy_compact(const uint32_t (&q)[(T + 3
 // q[PR]: packed position words.  Updated in place.  action: 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT
 // (state.py:31-34).
 template <int S, int T>
-__device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t action) {
-    if constexpr (padded_board(S)) slide_padded<S, T>(q, walls, action);
-    else slide_compact<S, T>(q, walls, action);
+__device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t h, uint32_t f) {
+    if constexpr (padded_board(S)) slide_padded<S, T>(q, walls, h, f);
+    else slide_compact<S, T>(q, walls, h, f);
 }
+// the h / f bits of the four actions of a thread's envs, one per byte (SWAR decode)
+__device__ __forceinline__ uint32_t actions_h4(uint32_t act4) { return (act4 >> 1) & 0x01010101u; }
+__device__ __forceinline__ uint32_t actions_f4(uint32_t act4) { return ~act4 & 0x01010101u; }
 template <int S, int T>
 __device__ __forceinline__ uint64_t occupancy(const uint32_t (&q)[(T + 3) / 4]) {
     if constexpr (padded_board(S)) return occupancy_padded<S, T>(q);

@@ -15,7 +15,25 @@
 
 namespace ts {
 
-constexpr int STEP_THREADS = 256;
+#ifndef TS_STEP_THREADS
+#define TS_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = TS_STEP_THREADS;
+
+// Resident CTAs per SM requested from ptxas.  The kernel needs every warp it can get to
+// cover the load latency at the top of each thread (measured: 8 CTAs x 256 threads = full
+// occupancy runs the 6x6/4-tile step 15% faster than the 40-register default), but only the
+// variants that fit 32 registers without spilling are forced there.
+template <int S, int T, int GOAL, bool AR, int CW>
+constexpr int step_min_blocks() {
+#ifdef TS_STEP_MINBLOCKS
+    return TS_STEP_MINBLOCKS;
+#else
+    if (padded_board(S) && T <= 4 && GOAL == TS_GOAL_ORDERED && CW == 1) return 8;
+    if (T <= 4) return 6;
+    return 4;
+#endif
+}
 
 // bit 7 of every byte of the result = (byte of a) >= (byte of b); b given as its low 7 bits
 // (b_lo) and its bit 7 (b_hi), both replicated per byte
@@ -27,16 +45,18 @@ __device__ __forceinline__ uint32_t swar_ge_u8(uint32_t a, uint32_t b_lo, uint32
 // AR: auto-reset on (flags are write-only) / off (done envs are frozen and report STALE)
 // CW: bytes of the step counter (1: SWAR bookkeeping, 4: per-env)
 template <int S, int T, int GOAL, bool AR, int CW>
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constant__ ts_step_args a) {
+__global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR, CW>())) step_kernel(const __grid_constant__ ts_step_args a) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S);
     constexpr int NWORDS = (NB + 3) / 4;
 
-    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
-    size_t g = (size_t)blockIdx.x * STEP_THREADS + threadIdx.x;
+    // 32-bit group index: every address below is base + g * constant, one IMAD.WIDE each
+    // (ts_step rejects capacities of 2^32 groups or more)
+    const uint32_t n_groups = (uint32_t)((a.n_envs + GROUP - 1) / GROUP);
+    uint32_t g = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (g >= n_groups) return;
-    g += (size_t)a.first_env / GROUP;
+    g += (uint32_t)(a.first_env / GROUP);
     const size_t cap = (size_t)a.capacity;
-    const size_t e0 = g * GROUP;
+    const size_t e0 = (size_t)g * GROUP;
 
     // ---- loads (all issued before first use) ------------------------------------------------
     uint32_t praw[PW];
@@ -65,6 +85,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     uint32_t to7 = 0;        // per byte: bit 7 = timeout (CW == 4 path fills it per env)
     float rew[GROUP];
     const bool can_win = a.never_win == 0;
+    const uint32_t h4 = actions_h4(act4), f4 = actions_f4(act4);
 
 #pragma unroll
     for (int e = 0; e < GROUP; ++e) {
@@ -73,9 +94,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
         walls.get(e, bw);
-        const uint32_t action = (act4 >> (8 * e)) & 3u;
-
-        slide_env<S, T>(q, board64(bw), action);
+        slide_env<S, T>(q, board64(bw), (h4 >> (8 * e)) & 0xFFu, (f4 >> (8 * e)) & 0xFFu);
 
         bool moved = false;
 #pragma unroll
@@ -94,7 +113,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         rew[e] = won ? a.r_win : (moved ? a.r_step : a.r_invalid);
         uint32_t wm = won ? F_WON : 0u;
         if (!moved) wm |= F_INVALID;
-        wm4 = wm * (1u << (8 * e)) + wm4;
+        wm4 = mad_u32(wm, 1u << (8 * e), wm4);
         if constexpr (CW == 4) {
             cntw[e] += 1u;
             if ((int)cntw[e] >= a.max_steps) to7 |= 0x80u << (8 * e);

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_v
             uint32_t q[PR];
 #pragma unroll
             for (int w = 0; w < PR; ++w) q[w] = q0[w];
-            slide_env<S, T>(q, wb, d);
+            slide_env<S, T>(q, wb, d >> 1, (d & 1u) ^ 1u);
             bool moved = false;
 #pragma unroll
             for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
