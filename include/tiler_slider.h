@@ -31,7 +31,11 @@
  *    k of a buffer starts at byte offset ts_plane_offset(nb,k)*capacity and holds one element
  *    per env.  S <= 6: BS = PS = S+1 and a WALL board also has column S of every row and all
  *    bits past the last row set (sentinels that end a slide; ts_encode / ts_synth write
- *    them).  S >= 7: BS = S, PS = 16, no sentinels.
+ *    them).  S = 7, 8: BS = S, PS = 16, no sentinels.
+ *  - wide boards (S >= 9) do not use planes: walls = u16 [env][action 0..3][16 lines], the
+ *    board pre-oriented per action (line = row for LEFT/RIGHT, column for UP/DOWN; bit o = the
+ *    cell at distance o from the end the move goes AWAY from), 128 bytes per env of which a
+ *    step reads one 32-byte sector; set-goal target board = u16 [env][16 rows]; PS = 16.
  *  - step_count: uint8 per env when max_steps <= 255 (count_bytes = 1), else int32
  *    (count_bytes = 4).
  *  - actions: uint8 per env, 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (state.py:31-34).
@@ -82,6 +86,8 @@ int ts_pos_bytes(int n_tiles);
 int ts_board_bytes(int size);
 int ts_board_stride(int size);   /* BS: bit index of cell (r,c) in a board = r*BS + c */
 int ts_pos_stride(int size);     /* PS: position byte of a tile at (r,c) = r*PS + c */
+int ts_walls_bytes(int size);    /* bytes per env of the walls buffer (its size = this * capacity) */
+int ts_target_board_bytes(int size); /* bytes per env of the set-goal target board buffer */
 int ts_plane_count(int n_bytes);
 int ts_plane_width(int n_bytes, int k);
 int ts_plane_offset(int n_bytes, int k);

@@ -89,6 +89,13 @@ SHAPES = [  # S, T, W, multi, N, K, max_steps
     (8, 8, 12, True, 4096, 64, 100),
     (8, 6, 20, False, 2048, 64, 13),
     (7, 7, 4, False, 2048, 64, 100),
+    (12, 8, 36, True, 8192, 128, 100),     # config 4 (wide boards)
+    (12, 8, 36, False, 4096, 64, 100),
+    (9, 4, 20, True, 2048, 64, 9),
+    (10, 3, 0, False, 2048, 64, 100),
+    (16, 8, 60, True, 2048, 64, 300),
+    (16, 5, 100, False, 2048, 64, 100),
+    (13, 1, 40, False, 2048, 64, 100),
 ]
 
 
@@ -152,7 +159,8 @@ def test_ordered_goal_length_mismatch_never_wins(ts):
 
 def test_observation_valid_moves_goal(ts):
     rng = np.random.default_rng(11)
-    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (4, 2, 2, True), (8, 8, 10, True)]:
+    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (4, 2, 2, True), (8, 8, 10, True),
+                           (12, 8, 36, True), (12, 8, 36, False), (16, 3, 50, False)]:
         N, K = 256, 12
         blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
         actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
@@ -203,7 +211,7 @@ def test_synth_well_formed_and_shard_invariant(ts):
 def test_synthetic_rollout_vs_oracle(ts):
     """The bench workload itself: device-generated puzzles decoded to the host and replayed by
     the oracle (config 2 and config 3 shapes)."""
-    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False)]:
+    for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (12, 8, 36, True)]:
         N, K = 8192, 128
         env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, seed=1002, max_steps=100, auto_reset=True,
                                                  track_terminal=True)

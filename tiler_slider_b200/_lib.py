@@ -75,6 +75,8 @@ SYMBOLS = {
     "ts_board_bytes": (C.c_int, [C.c_int]),
     "ts_board_stride": (C.c_int, [C.c_int]),
     "ts_pos_stride": (C.c_int, [C.c_int]),
+    "ts_walls_bytes": (C.c_int, [C.c_int]),
+    "ts_target_board_bytes": (C.c_int, [C.c_int]),
     "ts_plane_count": (C.c_int, [C.c_int]),
     "ts_plane_width": (C.c_int, [C.c_int, C.c_int]),
     "ts_plane_offset": (C.c_int, [C.c_int, C.c_int]),

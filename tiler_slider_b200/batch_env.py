@@ -73,8 +73,9 @@ class BatchedTilerSliderEnv:
         self.count_bytes = 1 if self.max_steps <= 255 else 4
         cap, dev = self.capacity, self.device
         u8 = torch.uint8
-        self._walls = torch.zeros(cap * self.board_bytes, dtype=u8, device=dev)
-        tbytes = self.pos_bytes if self.goal_mode == GOAL_ORDERED else self.board_bytes
+        self.wide = self.size > 8
+        self._walls = torch.zeros(cap * self._lib.ts_walls_bytes(self.size), dtype=u8, device=dev)
+        tbytes = self.pos_bytes if self.goal_mode == GOAL_ORDERED else self._lib.ts_target_board_bytes(self.size)
         self._targets = torch.zeros(cap * tbytes, dtype=u8, device=dev)
         self._init = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev)
         self._pos = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev)
@@ -324,6 +325,10 @@ class BatchedTilerSliderEnv:
     def _board_cells(self, buf: torch.Tensor) -> torch.Tensor:
         """Unpack a plane-layout bitboard buffer to bool[N, S*S] (load-time / debugging aid)."""
         nb, cap, n = self.board_bytes, self.capacity, self.n_envs
+        if self.wide:   # u16 lines: walls [env][action][16] (action 3 = rows, bit c), targets [env][16]
+            lines = buf.view(torch.int16).view(cap, -1)[:n, -16:].to(torch.int32) & 0xFFFF
+            bits = (lines.unsqueeze(-1) >> torch.arange(16, device=buf.device)) & 1
+            return bits[:, : self.size, : self.size].reshape(n, self.size * self.size).bool()
         cols = []
         for k in range(self._lib.ts_plane_count(nb)):
             w, off = self._lib.ts_plane_width(nb, k), self._lib.ts_plane_offset(nb, k)

@@ -18,6 +18,9 @@ namespace ts {
     cudaError_t goal_dispatch_s##S(const ts_goal_args&, cudaStream_t);
 TS_DECL(1) TS_DECL(2) TS_DECL(3) TS_DECL(4) TS_DECL(5) TS_DECL(6) TS_DECL(7) TS_DECL(8)
 #undef TS_DECL
+cudaError_t wide_step_dispatch(const ts_step_args&, cudaStream_t);
+cudaError_t wide_valid_dispatch(const ts_valid_args&, cudaStream_t);
+cudaError_t wide_goal_dispatch(const ts_goal_args&, cudaStream_t);
 
 static thread_local char g_err[256] = "ok";
 static int fail(int code, const char* fmt, ...) {
@@ -70,19 +73,72 @@ __device__ __forceinline__ int wall_bit(const uint8_t* blocked_cells, int S, int
     return blocked_cells[r * S + c] ? 1 : 0;
 }
 
+// Write the wall board(s) of one env from a 0/1 cell map (all three board classes).
+__device__ void store_walls(uint8_t* d_walls, size_t cap, size_t env, int S, const uint8_t* cellmap) {
+    if (wide_board(S)) {
+        uint16_t* w = reinterpret_cast<uint16_t*>(d_walls) + env * 64;   // [action][line]
+        for (int l = 0; l < 16; ++l) {
+            uint32_t up = 0, down = 0, left = 0, right = 0;
+            if (l < S)
+                for (int k = 0; k < S; ++k) {
+                    if (cellmap[k * S + l]) { down |= 1u << k; up |= 1u << (S - 1 - k); }      // column l
+                    if (cellmap[l * S + k]) { right |= 1u << k; left |= 1u << (S - 1 - k); }   // row l
+                }
+            w[0 * 16 + l] = (uint16_t)up; w[1 * 16 + l] = (uint16_t)down;
+            w[2 * 16 + l] = (uint16_t)left; w[3 * 16 + l] = (uint16_t)right;
+        }
+        return;
+    }
+    const int nb = board_bytes(S);
+    for (int b = 0; b < nb; ++b) {
+        uint32_t v = 0;
+        for (int k = 0; k < 8; ++k) v |= (uint32_t)wall_bit(cellmap, S, 8 * b + k) << k;
+        d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
+    }
+}
+
+// Write the set-goal target board of one env from its target cells (row*S+col each).
+__device__ void store_target_board(uint8_t* d_tb, size_t cap, size_t env, int S, int T, const int* cells, int n) {
+    if (wide_board(S)) {
+        uint16_t rows[16];
+        for (int r = 0; r < 16; ++r) rows[r] = 0;
+        for (int t = 0; t < n; ++t) rows[cells[t] / S] |= (uint16_t)(1u << (cells[t] % S));
+        int distinct = 0;
+        for (int r = 0; r < 16; ++r) distinct += __popc((uint32_t)rows[r]);
+        // the wide kernels test "every tile on a target cell"; that is set equality only when
+        // there are exactly T distinct targets -- otherwise the goal is unreachable
+        // (state.py:185-186), encoded as an empty board
+        uint16_t* o = reinterpret_cast<uint16_t*>(d_tb) + env * 16;
+        for (int r = 0; r < 16; ++r) o[r] = distinct == T ? rows[r] : (uint16_t)0;
+        return;
+    }
+    const int nb = board_bytes(S), bs = board_stride(S);
+    for (int b = 0; b < nb; ++b) {
+        uint32_t v = 0;
+        for (int t = 0; t < n; ++t) {
+            const int bit = (cells[t] / S) * bs + (cells[t] % S);
+            if ((bit >> 3) == b) v |= 1u << (bit & 7);
+        }
+        d_tb[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
+    }
+}
+
+__device__ __forceinline__ bool wall_at(const uint8_t* d_walls, size_t cap, size_t env, int S, int r, int c) {
+    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_walls)[env * 64 + 3 * 16 + r] >> c) & 1;
+    return board_bit(d_walls, board_bytes(S), cap, env, r * board_stride(S) + c);
+}
+__device__ __forceinline__ bool target_at(const uint8_t* d_tb, size_t cap, size_t env, int S, int r, int c) {
+    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_tb)[env * 16 + r] >> c) & 1;
+    return board_bit(d_tb, board_bytes(S), cap, env, r * board_stride(S) + c);
+}
+
 // ---- K1 encode --------------------------------------------------------------------------------
 __global__ void encode_kernel(const ts_encode_args a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_envs) return;
     const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
-    const int S = a.size, T = a.n_tiles, NT = a.n_targets, nb = board_bytes(S), pw = pos_bytes(T);
-    const int bs = board_stride(S), ps = pos_stride(S);
-    const uint8_t* blk = a.d_blocked + (size_t)i * S * S;
-    for (int b = 0; b < nb; ++b) {
-        uint32_t v = 0;
-        for (int k = 0; k < 8; ++k) v |= (uint32_t)wall_bit(blk, S, 8 * b + k) << k;
-        a.d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
-    }
+    const int S = a.size, T = a.n_tiles, NT = a.n_targets, pw = pos_bytes(T), ps = pos_stride(S);
+    store_walls(a.d_walls, cap, env, S, a.d_blocked + (size_t)i * S * S);
     const uint8_t* tl = a.d_tiles + (size_t)i * T * 2;
     for (int t = 0; t < pw; ++t) {
         const uint8_t v = t < T ? (uint8_t)(tl[2 * t] * ps + tl[2 * t + 1]) : 0;
@@ -94,14 +150,10 @@ __global__ void encode_kernel(const ts_encode_args a) {
         for (int t = 0; t < pw; ++t)
             a.d_targets_packed[env * pw + t] = t < NT ? (uint8_t)(tg[2 * t] * ps + tg[2 * t + 1]) : 0;
     } else {
-        for (int b = 0; b < nb; ++b) {
-            uint32_t v = 0;
-            for (int t = 0; t < NT; ++t) {
-                const int bit = tg[2 * t] * bs + tg[2 * t + 1];
-                if ((bit >> 3) == b) v |= 1u << (bit & 7);
-            }
-            a.d_targets_packed[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
-        }
+        int cells[MAX_SIZE * MAX_SIZE];
+        const int n = NT < MAX_SIZE * MAX_SIZE ? NT : MAX_SIZE * MAX_SIZE;
+        for (int t = 0; t < n; ++t) cells[t] = tg[2 * t] * S + tg[2 * t + 1];
+        store_target_board(a.d_targets_packed, cap, env, S, T, cells, n);
     }
 }
 
@@ -117,7 +169,7 @@ __global__ void synth_kernel(const ts_synth_args a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_envs) return;
     const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
-    const int S = a.size, T = a.n_tiles, W = a.n_walls, nb = board_bytes(S), pw = pos_bytes(T);
+    const int S = a.size, T = a.n_tiles, W = a.n_walls, pw = pos_bytes(T);
     const int cells = S * S, draws = W + 2 * T;
     uint64_t rng = a.seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(a.env_index_base + i + 1));
     splitmix64(rng);
@@ -130,22 +182,11 @@ __global__ void synth_kernel(const ts_synth_args a) {
         perm[d] = perm[j];
         perm[j] = t;
     }
-    const int bs = board_stride(S), ps = pos_stride(S);
+    const int ps = pos_stride(S);
     uint8_t cellmap[MAX_SIZE * MAX_SIZE];
     for (int c = 0; c < cells; ++c) cellmap[c] = 0;
     for (int d = 0; d < W; ++d) cellmap[perm[d]] = 1;
-    uint8_t tbytes[MAX_SIZE * MAX_SIZE / 8 + 8];
-    for (int b = 0; b < nb; ++b) {
-        uint32_t v = 0;
-        for (int k = 0; k < 8; ++k) v |= (uint32_t)wall_bit(cellmap, S, 8 * b + k) << k;
-        a.d_walls[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
-        tbytes[b] = 0;
-    }
-    for (int t = 0; t < T; ++t) {
-        const int c = perm[W + T + t];
-        const int bit = (c / S) * bs + (c % S);
-        tbytes[bit >> 3] |= (uint8_t)(1u << (bit & 7));
-    }
+    store_walls(a.d_walls, cap, env, S, cellmap);
     for (int t = 0; t < pw; ++t) {
         uint8_t v = 0;
         if (t < T) { const int c = perm[W + t]; v = (uint8_t)((c / S) * ps + (c % S)); }
@@ -159,22 +200,23 @@ __global__ void synth_kernel(const ts_synth_args a) {
             a.d_targets_packed[env * pw + t] = v;
         }
     } else {
-        for (int b = 0; b < nb; ++b) a.d_targets_packed[board_byte_addr(nb, cap, env, b)] = tbytes[b];
+        int tcells[MAX_TILES];
+        for (int t = 0; t < T; ++t) tcells[t] = perm[W + T + t];
+        store_target_board(a.d_targets_packed, cap, env, S, T, tcells, T);
     }
 }
 
 // ---- K3 observe ---------------------------------------------------------------------------------
 // thread = one cell of one env; a warp writes 32 cells x 3 channels = 384 contiguous bytes.
 __global__ void observe_kernel(const ts_observe_args a) {
-    const int S = a.size, T = a.n_tiles, cells = S * S, nb = board_bytes(S), pw = pos_bytes(T);
+    const int S = a.size, T = a.n_tiles, cells = S * S, pw = pos_bytes(T);
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_envs * cells) return;
     const int64_t i = idx / cells;
     const int cell = (int)(idx - i * cells);
     const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
-    const int bit = (cell / S) * board_stride(S) + (cell % S);
     const uint8_t rc = (uint8_t)((cell / S) * pos_stride(S) + (cell % S));
-    const float ch0 = board_bit(a.d_walls, nb, cap, env, bit) ? 1.0f : 0.0f;
+    const float ch0 = wall_at(a.d_walls, cap, env, S, cell / S, cell % S) ? 1.0f : 0.0f;
     float ch1 = 0.0f, ch2 = 0.0f;
     const bool ordered = a.goal_mode == TS_GOAL_ORDERED;
     for (int t = 0; t < T; ++t)
@@ -183,7 +225,7 @@ __global__ void observe_kernel(const ts_observe_args a) {
         for (int t = 0; t < T; ++t)
             if (a.d_targets_packed[env * pw + t] == rc) ch2 = (float)(t + 1);
     } else {
-        ch2 = board_bit(a.d_targets_packed, nb, cap, env, bit) ? 1.0f : 0.0f;
+        ch2 = target_at(a.d_targets_packed, cap, env, S, cell / S, cell % S) ? 1.0f : 0.0f;
     }
     float* o = a.d_obs + (size_t)idx * 3;
     o[0] = ch0; o[1] = ch1; o[2] = ch2;
@@ -204,7 +246,9 @@ int ts_pos_stride(int size) { return pos_stride(size); }
 int ts_plane_count(int n_bytes) { return plane_count(n_bytes); }
 int ts_plane_width(int n_bytes, int k) { return plane_width(n_bytes, k); }
 int ts_plane_offset(int n_bytes, int k) { return plane_offset(n_bytes, k); }
-int ts_supported(int size, int n_tiles) { return size >= 1 && size <= 8 && n_tiles >= 1 && n_tiles <= MAX_TILES; }
+int ts_walls_bytes(int size) { return walls_bytes(size); }
+int ts_target_board_bytes(int size) { return target_board_bytes(size); }
+int ts_supported(int size, int n_tiles) { return size >= 1 && size <= MAX_SIZE && n_tiles >= 1 && n_tiles <= MAX_TILES; }
 
 int ts_encode(const ts_encode_args* a, void* stream) {
     if (!a) return fail(TS_E_NULL_POINTER, "null args");
@@ -263,7 +307,7 @@ int ts_step(const ts_step_args* a, void* stream) {
         case 6: e = step_dispatch_s6(args, st); break;
         case 7: e = step_dispatch_s7(args, st); break;
         case 8: e = step_dispatch_s8(args, st); break;
-        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+        default: e = wide_step_dispatch(args, st); break;
     }
     return cuda_result(e, "ts_step launch");
 }
@@ -296,7 +340,7 @@ int ts_valid_moves(const ts_valid_args* a, void* stream) {
         case 6: e = valid_dispatch_s6(*a, st); break;
         case 7: e = valid_dispatch_s7(*a, st); break;
         case 8: e = valid_dispatch_s8(*a, st); break;
-        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+        default: e = wide_valid_dispatch(*a, st); break;
     }
     return cuda_result(e, "ts_valid_moves launch");
 }
@@ -319,7 +363,7 @@ int ts_goal_check(const ts_goal_args* a, void* stream) {
         case 6: e = goal_dispatch_s6(*a, st); break;
         case 7: e = goal_dispatch_s7(*a, st); break;
         case 8: e = goal_dispatch_s8(*a, st); break;
-        default: return fail(TS_E_UNSUPPORTED, "size %d", a->size);
+        default: e = wide_goal_dispatch(*a, st); break;
     }
     return cuda_result(e, "ts_goal_check launch");
 }

@@ -1,0 +1,254 @@
+// ts_wide.cu -- step / valid-move / goal kernels for wide boards (9 <= S <= 16, T <= 8), the
+// shape of BASELINE config 4 (12x12, 8 tiles, dense walls).
+//
+// Results reproduced: GameState.move (explainrl/environment/state.py:120-170), is_won
+// (state.py:172-186), TilerSliderEnv.step bookkeeping (explainrl/environment/environment.py:
+// 119-143), reset (environment.py:89-97), get_valid_moves (environment.py:149-171).
+//
+// A wide board does not fit a 64-bit word, so the bitboard tricks of ts_common.cuh do not
+// apply.  Layout (env-major, one 32-byte sector per orientation):
+//   walls[env][a][line]  u16, a = action (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT): the board
+//                        pre-oriented for that move -- `line` is the row (LEFT/RIGHT) or the
+//                        column (UP/DOWN) and bit o is the o-th cell of that line counted
+//                        TOWARD the move direction's far end reversed, i.e. a slide always
+//                        goes toward higher bits.  The walls are static, so the four
+//                        orientations are written once by ts_encode / ts_synth; a step reads
+//                        exactly ONE 32-byte sector of them (select-source load), never all.
+//   tboard[env][row]     u16 target cells (set goal only)
+//   position byte        row*16 + col
+// Thread = one env.  The 16 line words of the chosen orientation and the occupancy lines
+// built from the tile positions live in shared memory as [word][thread] columns: a thread
+// only ever touches its own column, so the dynamic line index costs no bank conflict
+// (bank = thread % 32 whatever the line) and needs no barrier.
+#include "ts_common.cuh"
+#include "../../include/tiler_slider.h"
+
+namespace ts {
+
+constexpr int WIDE_THREADS = 256;
+
+struct WideSmem {
+    uint32_t w[8][WIDE_THREADS];   // wall lines, two 16-bit lines per word
+    uint32_t o[8][WIDE_THREADS];   // occupancy lines of the current move
+};
+
+template <int PW> __device__ __forceinline__ void ld_pos(const uint8_t* p, size_t env, uint32_t (&q)[(PW + 3) / 4]) {
+    if constexpr (PW == 1) q[0] = p[env];
+    else if constexpr (PW == 2) q[0] = reinterpret_cast<const uint16_t*>(p)[env];
+    else if constexpr (PW == 4) q[0] = reinterpret_cast<const uint32_t*>(p)[env];
+    else { const uint2 v = reinterpret_cast<const uint2*>(p)[env]; q[0] = v.x; q[1] = v.y; }
+}
+template <int PW> __device__ __forceinline__ void st_pos(uint8_t* p, size_t env, const uint32_t (&q)[(PW + 3) / 4]) {
+    if constexpr (PW == 1) p[env] = (uint8_t)q[0];
+    else if constexpr (PW == 2) reinterpret_cast<uint16_t*>(p)[env] = (uint16_t)q[0];
+    else if constexpr (PW == 4) reinterpret_cast<uint32_t*>(p)[env] = q[0];
+    else reinterpret_cast<uint2*>(p)[env] = make_uint2(q[0], q[1]);
+}
+
+__device__ __forceinline__ uint32_t half_of(uint32_t word, uint32_t half) {
+    return __byte_perm(word, 0, 0x4410u + half * 0x22u);   // half ? word >> 16 : word & 0xffff
+}
+
+// One slide of all T tiles of the calling thread's env.  `board` = the 32-byte orientation
+// sector for `action`.  q: position bytes (row*16+col), updated in place.
+template <int T>
+__device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
+    constexpr int PR = (T + 3) / 4;
+    const int tid = threadIdx.x;
+    const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
+    const uint4 b0 = __ldg(board), b1 = __ldg(board + 1);
+    sm.w[0][tid] = b0.x; sm.w[1][tid] = b0.y; sm.w[2][tid] = b0.z; sm.w[3][tid] = b0.w;
+    sm.w[4][tid] = b1.x; sm.w[5][tid] = b1.y; sm.w[6][tid] = b1.z; sm.w[7][tid] = b1.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm.o[k][tid] = 0;
+
+    // (line, offset) per byte: high nibble = line, low nibble = offset toward the move direction
+    const uint32_t ks = 0x01010101u * (uint32_t)(S - 1);
+    uint32_t Q[PR], ACC[PR];
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        uint32_t x = h ? q[w] : swap_nibbles(q[w]);
+        if (f) x = (x & 0xF0F0F0F0u) | (ks - (x & 0x0F0F0F0Fu));
+        Q[w] = x;
+        ACC[w] = 0;
+    }
+    uint32_t line[T], off[T];
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t b = byte_of<i % 4>(Q[i / 4]);
+        line[i] = b >> 4;
+        off[i] = b & 15u;
+        sm.o[line[i] >> 1][tid] |= 1u << (off[i] + 16u * (line[i] & 1u));
+    });
+    const uint32_t sentinel = 1u << S;
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t ww = half_of(sm.w[line[i] >> 1][tid], line[i] & 1u) | sentinel;
+        const uint32_t oo = half_of(sm.o[line[i] >> 1][tid], line[i] & 1u);
+        const uint32_t x = ww >> (off[i] + 1u);          // walls past the tile; the sentinel ends the line
+        const uint32_t run = (x - 1u) & ~x;              // cells before the first wall
+        ACC[i / 4] += (uint32_t)__popc(run & ~(oo >> (off[i] + 1u))) << (8 * (i % 4));
+    });
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        uint32_t x = Q[w] + ACC[w];                      // offset += #empty cells; never carries (<= S-1)
+        if (f) x = (x & 0xF0F0F0F0u) | (ks - (x & 0x0F0F0F0Fu));
+        q[w] = h ? x : swap_nibbles(x);
+    }
+    if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
+}
+
+// set goal: every tile stands on a target cell (ts_encode guarantees the target board is empty
+// unless it has exactly T distinct cells, so this is set equality; state.py:185-186)
+template <int T>
+__device__ __forceinline__ bool on_targets_wide(const uint32_t (&q)[(T + 3) / 4], const uint8_t* tboard, size_t env) {
+    const uint16_t* rows = reinterpret_cast<const uint16_t*>(tboard) + env * 16;
+    bool all = true;
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t b = byte_of<i % 4>(q[i / 4]);
+        all &= ((__ldg(rows + (b >> 4)) >> (b & 15u)) & 1u) != 0;
+    });
+    return all;
+}
+
+template <int T, int GOAL>
+__global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_constant__ ts_step_args a) {
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
+    __shared__ WideSmem sm;
+    const int64_t i = (int64_t)blockIdx.x * WIDE_THREADS + threadIdx.x;
+    if (i >= a.n_envs) return;
+    const size_t env = (size_t)(a.first_env + i);
+    const uint32_t action = a.d_actions[env] & 3u;
+    uint32_t q0[PR], q[PR];
+    ld_pos<PW>(a.d_pos, env, q0);
+#pragma unroll
+    for (int w = 0; w < PR; ++w) q[w] = q0[w];
+    uint32_t count = a.count_bytes == 1 ? (uint32_t)reinterpret_cast<const uint8_t*>(a.d_step_count)[env]
+                                        : reinterpret_cast<const uint32_t*>(a.d_step_count)[env];
+    const bool stale = !a.auto_reset && (a.d_flags[env] & F_DONE);
+
+    slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + (env * 4 + action) * 2, a.size, action);
+
+    bool moved = false, won = a.never_win == 0;
+#pragma unroll
+    for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
+    if constexpr (GOAL == TS_GOAL_ORDERED) {
+        uint32_t tq[PR];
+        ld_pos<PW>(a.d_targets_packed, env, tq);
+#pragma unroll
+        for (int w = 0; w < PR; ++w) won &= q[w] == tq[w];
+    } else {
+        won &= on_targets_wide<T>(q, a.d_targets_packed, env);
+    }
+    count += 1u;
+    const bool timeout = (int)count >= a.max_steps;
+    bool done = won || timeout;
+    uint32_t flags = (done ? F_DONE : 0u) | (won ? F_WON : 0u) | (moved ? 0u : F_INVALID) | (timeout ? F_TIMEOUT : 0u);
+    float reward = won ? a.r_win : (moved ? a.r_step : a.r_invalid);
+    if (stale) {   // frozen: the reference raises here (environment.py:113-114)
+        flags = F_DONE | F_STALE;
+        reward = 0.0f;
+        count -= 1u;
+        done = true;
+#pragma unroll
+        for (int w = 0; w < PR; ++w) q[w] = q0[w];
+    }
+    if (done) {
+        if (a.d_terminal_pos) st_pos<PW>(a.d_terminal_pos, env, q);
+        if (a.auto_reset) {   // environment.py:89-97
+            ld_pos<PW>(a.d_init, env, q);
+            count = 0;
+        }
+    }
+    st_pos<PW>(a.d_pos, env, q);
+    if (a.count_bytes == 1) reinterpret_cast<uint8_t*>(a.d_step_count)[env] = (uint8_t)count;
+    else reinterpret_cast<uint32_t*>(a.d_step_count)[env] = count;
+    a.d_reward[env] = reward;
+    if (a.d_done) a.d_done[env] = done ? 1 : 0;
+    if (a.d_flags) a.d_flags[env] = (uint8_t)flags;
+}
+
+template <int T>
+__global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_constant__ ts_valid_args a) {
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
+    __shared__ WideSmem sm;
+    const int64_t i = (int64_t)blockIdx.x * WIDE_THREADS + threadIdx.x;
+    if (i >= a.n_envs) return;
+    const size_t env = (size_t)(a.first_env + i);
+    uint32_t q0[PR];
+    ld_pos<PW>(a.d_pos, env, q0);
+    uint32_t mask = 0;
+    for (uint32_t d = 0; d < 4; ++d) {
+        uint32_t q[PR];
+#pragma unroll
+        for (int w = 0; w < PR; ++w) q[w] = q0[w];
+        slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + (env * 4 + d) * 2, a.size, d);
+        bool moved = false;
+#pragma unroll
+        for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
+        mask |= (moved ? 1u : 0u) << d;
+    }
+    a.d_mask[env] = (uint8_t)mask;
+}
+
+template <int T>
+__global__ void __launch_bounds__(WIDE_THREADS) wide_goal_kernel(const __grid_constant__ ts_goal_args a) {
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
+    const int64_t i = (int64_t)blockIdx.x * WIDE_THREADS + threadIdx.x;
+    if (i >= a.n_envs) return;
+    const size_t env = (size_t)(a.first_env + i);
+    uint32_t q[PR];
+    ld_pos<PW>(a.d_pos, env, q);
+    bool won = a.never_win == 0;
+    if (a.goal_mode == TS_GOAL_ORDERED) {
+        uint32_t tq[PR];
+        ld_pos<PW>(a.d_targets_packed, env, tq);
+#pragma unroll
+        for (int w = 0; w < PR; ++w) won &= q[w] == tq[w];
+    } else {
+        won &= on_targets_wide<T>(q, a.d_targets_packed, env);
+    }
+    a.d_won[env] = won ? 1 : 0;
+}
+
+template <int T> static cudaError_t launch_wide_step(const ts_step_args& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n_envs + WIDE_THREADS - 1) / WIDE_THREADS);
+    if (a.goal_mode == TS_GOAL_ORDERED) wide_step_kernel<T, TS_GOAL_ORDERED><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    else wide_step_kernel<T, TS_GOAL_SET><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define TS_WIDE_SWITCH(CALL)                                   \
+    switch (a.n_tiles) {                                       \
+        case 1: CALL(1); break; case 2: CALL(2); break;        \
+        case 3: CALL(3); break; case 4: CALL(4); break;        \
+        case 5: CALL(5); break; case 6: CALL(6); break;        \
+        case 7: CALL(7); break; case 8: CALL(8); break;        \
+        default: return cudaErrorInvalidValue;                 \
+    }
+
+cudaError_t wide_step_dispatch(const ts_step_args& a, cudaStream_t st) {
+#define CALL(T) return launch_wide_step<T>(a, st)
+    TS_WIDE_SWITCH(CALL)
+#undef CALL
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t wide_valid_dispatch(const ts_valid_args& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n_envs + WIDE_THREADS - 1) / WIDE_THREADS);
+#define CALL(T) wide_valid_kernel<T><<<blocks, WIDE_THREADS, 0, st>>>(a)
+    TS_WIDE_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t wide_goal_dispatch(const ts_goal_args& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n_envs + WIDE_THREADS - 1) / WIDE_THREADS);
+#define CALL(T) wide_goal_kernel<T><<<blocks, WIDE_THREADS, 0, st>>>(a)
+    TS_WIDE_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+}  // namespace ts
