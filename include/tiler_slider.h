@@ -198,6 +198,44 @@ typedef struct ts_goal_args {
 int ts_goal_check(const ts_goal_args *a, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Breadth-first state-space expansion (BASELINE config 5; no reference counterpart -- the
+ * successor function is GameState.move, state.py:120-170, the goal test is_won,
+ * state.py:172-186; boards of size <= 8).
+ *
+ * State key (uint64): canonical position word in the low bits (ordered goal: the position
+ * bytes; set goal: the bytes sorted ascending), puzzle id in bits 32..62 when n_tiles <= 4
+ * (n_tiles > 4: one puzzle only), bit 63 = "meets the goal" (ignored by dedup).
+ * TS_BFS_NONE marks a move that changed nothing.  The puzzle table is a packed batch
+ * (walls / targets / init of `puzzle_capacity` stride, as written by ts_encode).
+ *
+ *   ts_bfs_seed              d_out_keys[i] = key of puzzle i's initial state, i < n_items
+ *   ts_bfs_expand        K4  d_out_keys[4*i+d] = successor of d_in_keys[i] under move d
+ *   ts_bfs_partition_count   d_counts[r] += #keys of d_in_keys owned by rank r = hash(key) % n_ranks
+ *   ts_bfs_partition_scatter d_out_keys bucketed by owner; d_counts[r] = write cursor of bucket r
+ *                            (initialise to the exclusive prefix sum of the counts)
+ *   ts_bfs_hash_insert   K5  insert d_in_keys into the open-addressing table d_table
+ *                            (table_capacity a power of two, empty = TS_BFS_NONE); keys not
+ *                            seen before are appended to d_out_keys; d_counts[0] = append
+ *                            cursor, d_counts[1] += #goal successors seen, d_counts[2] = 1 on
+ *                            overflow of the table or of out_capacity
+ * The exchange between partition and insert is an NCCL all-to-all done by the caller.
+ * ------------------------------------------------------------------------------------- */
+#define TS_BFS_NONE 0xFFFFFFFFFFFFFFFFull
+#define TS_BFS_WON_BIT 0x8000000000000000ull
+typedef struct ts_bfs_args {
+    int32_t size, n_tiles, goal_mode, never_win, n_ranks, reserved;
+    int64_t n_items, puzzle_capacity, table_capacity, out_capacity;
+    const uint8_t *d_walls, *d_targets_packed, *d_init;
+    const uint64_t *d_in_keys;
+    uint64_t *d_out_keys, *d_table, *d_counts;
+} ts_bfs_args;
+int ts_bfs_seed(const ts_bfs_args *a, void *stream);
+int ts_bfs_expand(const ts_bfs_args *a, void *stream);
+int ts_bfs_partition_count(const ts_bfs_args *a, void *stream);
+int ts_bfs_partition_scatter(const ts_bfs_args *a, void *stream);
+int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * ts_step_host: the same step through HOST buffers (the call a host-side driver makes):
  * h_actions (pinned) -> device, ts_step, reward/done -> h_reward/h_done (pinned), pipelined in
  * chunks over the context's streams; returns after everything has landed.

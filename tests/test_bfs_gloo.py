@@ -1,0 +1,144 @@
+"""BFS driver logic (hash-partitioned frontier exchange, termination, per-puzzle statistics) on
+CPU over gloo with world_size 2.  The CUDA kernels are replaced by a stand-in built on the
+CPU oracle (test infrastructure); the product driver `tiler_slider_b200.bfs.BfsSolver` is the
+code under test.  Known answers: tests/golden/misc.json (plain BFS over the reference's move)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBfsKernels:
+    """Same interface as CudaBfsKernels, on CPU tensors, successor function = oracle move."""
+
+    def __init__(self, puzzles):
+        from oracle import oracle as orc
+        self.device = torch.device("cpu")
+        self.puzzles = puzzles
+        self.states = [orc.OracleState(p["size"], p["blocked"], p["tiles"], p["targets"], p["multi_color"]) for p in puzzles]
+
+    def _key(self, pid, st, won=False):
+        S = st.size
+        cells = [r * S + c for r, c in st.current_locations]
+        if not st.multi_color:
+            cells = sorted(cells)
+        k = sum(c << (8 * i) for i, c in enumerate(cells)) | (pid << 32)
+        return k - (1 << 63) if won else k
+
+    def seed(self):
+        return torch.tensor([self._key(i, st) for i, st in enumerate(self.states)], dtype=torch.int64)
+
+    def expand(self, frontier):
+        out = []
+        for key in frontier.tolist():
+            pid, st = (key >> 32) & 0x7FFFFFFF, None
+            st = self.states[pid]
+            cells = [(key >> (8 * i)) & 0xFF for i in range(st.n_tiles)]
+            for d in range(4):
+                st.set_locations([(c // st.size, c % st.size) for c in cells])
+                won = st.move(d)
+                k = self._key(pid, st, won)
+                out.append(-1 if (k & ~(-(1 << 63))) == key and not won else k)
+        return torch.tensor(out, dtype=torch.int64)
+
+    def partition(self, keys, n_ranks):
+        ks = [k for k in keys.tolist() if k != -1]
+        owner = [((k & 0x7FFFFFFFFFFFFFFF) * 2654435761 >> 7) % n_ranks for k in ks]
+        order = sorted(range(len(ks)), key=lambda i: owner[i])
+        return torch.tensor([ks[i] for i in order], dtype=torch.int64), [owner.count(r) for r in range(n_ranks)]
+
+    def new_table(self, capacity):
+        return set()
+
+    def insert(self, table, keys):
+        new, n_won = [], 0
+        for raw in keys.tolist():
+            if raw == -1:
+                continue
+            n_won += raw < 0
+            k = raw & 0x7FFFFFFFFFFFFFFF
+            if k not in table:
+                table.add(k)
+                new.append(raw)
+        return torch.tensor(new, dtype=torch.int64), n_won
+
+
+def _worker(rank, world, port, puzzles, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tiler_slider_b200.bfs import BfsSolver
+    res = BfsSolver(kernels=OracleBfsKernels(puzzles), n_puzzles=len(puzzles), table_capacity=1 << 16).solve()
+    if rank == 0:
+        q.put((res.n_states, res.levels, res.solve_depth, res.states_per_puzzle.tolist(),
+               res.solve_depth_per_puzzle.tolist(), res.generated))
+    dist.destroy_process_group()
+
+
+def _golden_bfs():
+    with open(os.path.join(ROOT, "tests", "golden", "misc.json")) as f:
+        return json.load(f)["bfs"]
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bfs_driver_over_gloo(world):
+    gold = {b["name"]: b for b in _golden_bfs()}
+    batch = [gold["puzzle_multi_111"], gold["puzzle_multi_180"]]     # same shape: 6x6, 3 ordered tiles
+    if world == 1:
+        sys.path.insert(0, ROOT)
+        from tiler_slider_b200.bfs import BfsSolver
+        res = BfsSolver(kernels=OracleBfsKernels(batch), n_puzzles=2, table_capacity=1 << 16).solve()
+        got = (res.n_states, res.levels, res.solve_depth, res.states_per_puzzle.tolist(),
+               res.solve_depth_per_puzzle.tolist(), res.generated)
+    else:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, world, 29533, batch, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = q.get(timeout=120)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    n_states, levels, solve_depth, spp, dpp, generated = got
+    assert spp == [558, 950] and dpp == [8, 13]
+    assert n_states == 558 + 950 and solve_depth == 8
+    la, lb = batch[0]["levels"], batch[1]["levels"]
+    want = [(la[i] if i < len(la) else 0) + (lb[i] if i < len(lb) else 0) for i in range(max(len(la), len(lb)))]
+    assert levels == want
+    assert generated == 4 * n_states
+
+
+def test_shard_and_reduce_over_gloo():
+    """The step path's only multi-rank logic: disjoint contiguous shards + a MAX reduce of the
+    per-rank time, as bench.py does it."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, 29534, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=60) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1:3] == (0, 501) and out[1][1:3] == (501, 1001)
+    assert out[0][3] == out[1][3] == 2.5
+
+
+def _shard_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tiler_slider_b200.batch_env import shard_range
+    lo, hi = shard_range(1001, rank, world)
+    t = torch.tensor([1.5 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, lo, hi, float(t.item())))
+    dist.destroy_process_group()

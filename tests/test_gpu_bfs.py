@@ -1,0 +1,81 @@
+"""BFS kernels on the GPU (ts_bfs_*): known answers recorded from a plain BFS over the
+reference's move (tests/golden/misc.json, SURVEY 8(c): 29 / 558 / 950 / 51 states, depths
+1 / 8 / 13 / 7) and random puzzle batches against the CPU oracle's BFS."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import tiler_slider_b200 as t
+    t.lib()
+    return t
+
+
+def puzzle_of(ts, b):
+    return ts.Puzzle(b["size"], [tuple(x) for x in b["blocked"]], [tuple(x) for x in b["tiles"]],
+                     [tuple(x) for x in b["targets"]], b["multi_color"])
+
+
+def test_known_answers_single_puzzles(ts, golden_misc):
+    from tiler_slider_b200.bfs import solve_puzzle
+    for b in golden_misc["bfs"]:
+        res = solve_puzzle(puzzle_of(ts, b), table_capacity=1 << 16)
+        assert (res.n_states, res.levels, res.solve_depth) == (b["n_states"], b["levels"], b["solve_depth"]), b["name"]
+        assert res.states_per_puzzle.tolist() == [b["n_states"]]
+        assert res.generated == 4 * b["n_states"]
+
+
+def test_batched_puzzles_share_one_table(ts, golden_misc):
+    from tiler_slider_b200.bfs import BfsSolver
+    gold = {b["name"]: b for b in golden_misc["bfs"]}
+    batch = [gold["puzzle_multi_111"], gold["puzzle_multi_180"]] * 3
+    res = BfsSolver([puzzle_of(ts, b) for b in batch], table_capacity=1 << 16).solve()
+    assert res.states_per_puzzle.tolist() == [558, 950] * 3
+    assert res.solve_depth_per_puzzle.tolist() == [8, 13] * 3
+    assert res.n_states == 3 * (558 + 950) and res.solve_depth == 8
+
+
+@pytest.mark.parametrize("S,T,W,multi,n", [(4, 2, 3, True, 48), (4, 3, 2, False, 32), (5, 2, 5, False, 32),
+                                            (6, 3, 9, True, 24), (3, 4, 1, True, 32), (7, 2, 12, True, 16),
+                                            (8, 2, 20, False, 16)])
+def test_random_batches_vs_oracle_bfs(ts, S, T, W, multi, n):
+    from tiler_slider_b200.bfs import BfsSolver
+    from tests.helpers import random_puzzles
+    rng = np.random.default_rng(S * 100 + T)
+    blocked, tiles, targets = random_puzzles(rng, n, S, T, W)
+    table = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi)
+    res = BfsSolver(table, table_capacity=1 << 20).solve()
+    want_states, want_depth, want_levels = [], [], {}
+    for e in range(n):
+        b = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+        st = orc.OracleState(S, b, tiles[e].tolist(), targets[e].tolist(), multi)
+        ns, lv, depth, _ = st.bfs(max_states=1 << 20)
+        want_states.append(ns)
+        want_depth.append(depth)
+        for d, c in enumerate(lv):
+            want_levels[d] = want_levels.get(d, 0) + c
+    assert res.states_per_puzzle.tolist() == want_states
+    assert res.solve_depth_per_puzzle.tolist() == want_depth
+    assert res.levels == [want_levels[d] for d in range(len(want_levels))]
+
+
+def test_more_than_four_tiles_single_puzzle(ts):
+    from tiler_slider_b200.bfs import solve_puzzle
+    p = ts.Puzzle(5, [(2, 2), (0, 3)], [(0, 0), (0, 1), (1, 0), (4, 4), (3, 3)], [(4, 0), (4, 1), (4, 2), (4, 3), (0, 4)], False)
+    res = solve_puzzle(p, table_capacity=1 << 20)
+    st = orc.OracleState(5, p.blocked_locations, p.initial_locations, p.target_locations, False)
+    ns, lv, depth, _ = st.bfs(max_states=1 << 20)
+    assert (res.n_states, res.levels, res.solve_depth) == (ns, lv, depth)
+
+
+def test_table_overflow_is_reported(ts, golden_misc):
+    from tiler_slider_b200.bfs import solve_puzzle
+    b = [x for x in golden_misc["bfs"] if x["name"] == "puzzle_multi_180"][0]
+    with pytest.raises(RuntimeError, match="table is full"):
+        solve_puzzle(puzzle_of(ts, b), table_capacity=256)

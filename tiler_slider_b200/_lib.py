@@ -67,6 +67,14 @@ class GoalArgs(C.Structure):
                 ("d_targets_packed", _vp), ("d_pos", _vp), ("d_won", _vp)]
 
 
+class BfsArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("never_win", _i32), ("n_ranks", _i32),
+                ("reserved", _i32),
+                ("n_items", _i64), ("puzzle_capacity", _i64), ("table_capacity", _i64), ("out_capacity", _i64),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_in_keys", _vp),
+                ("d_out_keys", _vp), ("d_table", _vp), ("d_counts", _vp)]
+
+
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ts_version": (C.c_int, []),
@@ -87,6 +95,11 @@ SYMBOLS = {
     "ts_observe": (C.c_int, [C.POINTER(ObserveArgs), _vp]),
     "ts_valid_moves": (C.c_int, [C.POINTER(ValidArgs), _vp]),
     "ts_goal_check": (C.c_int, [C.POINTER(GoalArgs), _vp]),
+    "ts_bfs_seed": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_expand": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_partition_count": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "ts_host_ctx_destroy": (C.c_int, [_vp]),
     "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _i64]),

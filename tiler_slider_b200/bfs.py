@@ -1,0 +1,205 @@
+"""Breadth-first state-space search over many puzzles at once (BASELINE config 5).
+
+The reference has no solver; the closest primitive is TilerSliderEnv.get_valid_moves
+(explainrl/environment/environment.py:149-171), which tries the four moves on copies.  Here
+the successor function is GameState.move (explainrl/environment/state.py:120-170) run by the
+sm_100a kernels of csrc/ts_bfs.cu, the goal test is is_won (state.py:172-186), and the visited
+set is an open-addressing hash table in HBM.  BFS itself is defined by this repo (parity
+unpinned); level histograms are pinned to a plain BFS over the reference's move
+(tests/golden/misc.json).
+
+Multi-GPU: every rank holds the (small, static) puzzle table and the slice of the visited set
+whose keys hash to it.  One exchange per depth:
+    expand local frontier (K4)  ->  bucket successors by owner rank  ->  all_to_all_single of
+    the bucket sizes, then of the u64 keys (NCCL over NVLink)  ->  insert into the local table
+    (K5); the keys that were new form the next local frontier  ->  all_reduce of the new-state
+    count (termination) and of the goal flag.
+A single puzzle has a tiny state space (51-950 states for real 6x6 levels), so the
+exchange only pays off for a batch of puzzles; key = puzzle id || canonical positions.
+
+The device kernels sit behind `CudaBfsKernels`; tests run the same driver logic on CPU
+tensors over gloo with a CPU stand-in for the kernels (tests/test_bfs_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+from ._lib import GOAL_SET, BfsArgs, check, lib
+from .batch_env import BatchedTilerSliderEnv
+from .puzzle import Puzzle
+
+NONE = -1                       # TS_BFS_NONE as int64
+WON_BIT = -(1 << 63)            # bit 63 as int64
+
+
+@dataclass
+class BfsResult:
+    n_states: int                              # reachable states, all puzzles, all ranks
+    levels: list[int]                          # new states per depth (depth 0 = the initial states)
+    solve_depth: int                           # first depth at which some successor met the goal (-1: none)
+    states_per_puzzle: torch.Tensor | None = None   # int64[P] reachable states per puzzle (this rank's share summed over ranks)
+    solve_depth_per_puzzle: torch.Tensor | None = None   # int32[P], -1 where unsolved within max_depth
+    generated: int = 0                         # successors generated (state x move), all ranks
+    per_level_seconds: list[float] = field(default_factory=list)
+
+
+class CudaBfsKernels:
+    """ctypes front-end of the ts_bfs_* entry points for one puzzle table."""
+
+    def __init__(self, table: BatchedTilerSliderEnv):
+        if table.size > 8:
+            raise ValueError("BFS supports board sizes up to 8")
+        if table.n_tiles > 4 and table.n_envs > 1:
+            raise ValueError("more than 4 tiles: the key has no room for a puzzle id, solve one puzzle at a time")
+        self.t, self.lib, self.device = table, lib(), table.device
+
+    def _args(self, **kw) -> BfsArgs:
+        t = self.t
+        base = dict(size=t.size, n_tiles=t.n_tiles, goal_mode=t.goal_mode, never_win=int(t.never_win), n_ranks=1,
+                    puzzle_capacity=t.capacity, d_walls=t._walls.data_ptr(), d_targets_packed=t._targets.data_ptr(),
+                    d_init=t._init.data_ptr())
+        base.update(kw)
+        return BfsArgs(**base)
+
+    def _call(self, fn, a: BfsArgs, what: str):
+        with torch.cuda.device(self.device):
+            check(fn(C.byref(a), torch.cuda.current_stream(self.device).cuda_stream), what)
+
+    def seed(self) -> torch.Tensor:
+        out = torch.empty(self.t.n_envs, dtype=torch.int64, device=self.device)
+        self._call(self.lib.ts_bfs_seed, self._args(n_items=self.t.n_envs, d_out_keys=out.data_ptr()), "ts_bfs_seed")
+        return out
+
+    def expand(self, frontier: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(4 * frontier.numel(), dtype=torch.int64, device=self.device)
+        self._call(self.lib.ts_bfs_expand, self._args(n_items=frontier.numel(), d_in_keys=frontier.data_ptr(),
+                                                      d_out_keys=out.data_ptr()), "ts_bfs_expand")
+        return out
+
+    def partition(self, keys: torch.Tensor, n_ranks: int) -> tuple[torch.Tensor, list[int]]:
+        """Bucket keys by owner rank (NONE dropped).  Returns (bucketed keys, bucket sizes)."""
+        counts = torch.zeros(n_ranks, dtype=torch.int64, device=self.device)
+        a = self._args(n_items=keys.numel(), n_ranks=n_ranks, d_in_keys=keys.data_ptr(), d_counts=counts.data_ptr())
+        self._call(self.lib.ts_bfs_partition_count, a, "ts_bfs_partition_count")
+        sizes = counts.tolist()                                    # host copy: the all-to-all needs split sizes
+        cursor = torch.cumsum(counts, 0) - counts
+        out = torch.empty(sum(sizes), dtype=torch.int64, device=self.device)
+        a = self._args(n_items=keys.numel(), n_ranks=n_ranks, d_in_keys=keys.data_ptr(), d_counts=cursor.data_ptr(),
+                       d_out_keys=out.data_ptr())
+        self._call(self.lib.ts_bfs_partition_scatter, a, "ts_bfs_partition_scatter")
+        return out, sizes
+
+    def new_table(self, capacity: int) -> torch.Tensor:
+        return torch.full((capacity,), NONE, dtype=torch.int64, device=self.device)
+
+    def insert(self, table: torch.Tensor, keys: torch.Tensor) -> tuple[torch.Tensor, int]:
+        """Insert keys; returns (keys that were new, with their goal bit; #goal successors seen)."""
+        out = torch.empty(keys.numel(), dtype=torch.int64, device=self.device)
+        counts = torch.zeros(4, dtype=torch.int64, device=self.device)
+        a = self._args(n_items=keys.numel(), table_capacity=table.numel(), out_capacity=out.numel(),
+                       d_in_keys=keys.data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
+                       d_counts=counts.data_ptr())
+        self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
+        n_new, n_won, overflow, _ = counts.tolist()
+        if overflow:
+            raise RuntimeError("BFS visited table is full: raise table_capacity")
+        return out[:n_new], n_won
+
+
+class BfsSolver:
+    """Level-synchronous BFS over a batch of puzzles, hash-partitioned over the ranks of `group`."""
+
+    def __init__(self, puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv | None = None, *, table_capacity: int = 1 << 22,
+                 device="cuda", group=None, kernels=None, n_puzzles: int | None = None):
+        if kernels is None:
+            table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else \
+                BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
+            kernels = CudaBfsKernels(table)
+            n_puzzles = table.n_envs
+        self.k = kernels
+        self.n_puzzles = int(n_puzzles)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if table_capacity & (table_capacity - 1):
+            raise ValueError("table_capacity must be a power of two")
+        self.table_capacity = table_capacity
+
+    # ---- one exchange: every key travels to the rank that owns it -------------------------
+    def _exchange(self, keys: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return keys[keys != NONE]
+        send, sizes = self.k.partition(keys, self.world)
+        send_sizes = torch.tensor(sizes, dtype=torch.int64, device=send.device)
+        recv_sizes = torch.empty_like(send_sizes)
+        dist.all_to_all_single(recv_sizes, send_sizes, group=self.group)
+        rs = recv_sizes.tolist()
+        recv = torch.empty(sum(rs), dtype=torch.int64, device=send.device)
+        dist.all_to_all_single(recv, send, rs, sizes, group=self.group)
+        return recv
+
+    def _sum(self, *vals: int) -> list[int]:
+        if self.world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.int64, device=self.k.device)
+        dist.all_reduce(t, group=self.group)
+        return t.tolist()
+
+    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True) -> BfsResult:
+        k, P = self.k, self.n_puzzles
+        table = k.new_table(self.table_capacity)
+        dev = k.device
+        states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
+        depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
+        single_puzzle_keys = getattr(k, "t", None) is not None and k.t.n_tiles > 4   # no id bits in the key
+
+        def pid_of(keys):
+            return torch.zeros_like(keys) if single_puzzle_keys else (keys >> 32) & 0x7FFFFFFF
+
+        # depth 0: every rank seeds all puzzles and keeps the keys it owns
+        seeds = k.seed()
+        mine = self._exchange(seeds) if self.world > 1 else seeds
+        if self.world > 1:   # every rank sent every seed: the owner received world copies; dedup does the rest
+            pass
+        frontier, _ = k.insert(table, mine)
+        levels, generated, solve_depth = [], 0, -1
+        n_new, = self._sum(frontier.numel())
+        levels.append(n_new)
+        if per_puzzle and frontier.numel():
+            states_pp.index_add_(0, pid_of(frontier), torch.ones_like(frontier))
+        depth = 0
+        while n_new > 0 and depth < max_depth:
+            depth += 1
+            succ = k.expand(frontier & ~WON_BIT)
+            recv = self._exchange(succ)
+            if per_puzzle and recv.numel():
+                won = recv[recv < 0]                         # bit 63 set: goal met (NONE already dropped)
+                if won.numel():
+                    d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
+                    depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
+            frontier, n_won = k.insert(table, recv)
+            n_new, n_won_all, gen = self._sum(frontier.numel(), n_won, 4 * (succ.numel() // 4))
+            generated += gen
+            if n_won_all and solve_depth < 0:
+                solve_depth = depth
+            if n_new:
+                levels.append(n_new)
+                if per_puzzle:
+                    states_pp.index_add_(0, pid_of(frontier), torch.ones_like(frontier))
+        if per_puzzle and self.world > 1:
+            dist.all_reduce(states_pp, group=self.group)
+            dist.all_reduce(depth_pp, op=dist.ReduceOp.MIN, group=self.group)
+        if per_puzzle:
+            depth_pp = torch.where(depth_pp >= (1 << 30), torch.full_like(depth_pp, -1), depth_pp)
+        return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
+                         solve_depth_per_puzzle=depth_pp, generated=generated)
+
+
+def solve_puzzle(puzzle: Puzzle, **kw) -> BfsResult:
+    """BFS of one puzzle on the current CUDA device."""
+    return BfsSolver([puzzle], **kw).solve()

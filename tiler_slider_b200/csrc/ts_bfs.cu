@@ -1,0 +1,273 @@
+// ts_bfs.cu -- breadth-first state-space expansion with hash-partitioned dedup (BASELINE
+// config 5).  The reference has no solver; the nearest thing is get_valid_moves
+// (explainrl/environment/environment.py:149-171), which tries the four moves on copies.  The
+// successor function here is exactly GameState.move (explainrl/environment/state.py:120-170)
+// through slide_env<S,T>, and the goal test is is_won (state.py:172-186).  BFS itself is
+// repo-defined (parity unpinned); its level histograms are pinned to a plain BFS over the
+// reference's move (tests/golden/misc.json).
+//
+// State key (u64):  bits 0..31 (T <= 4) or 0..62 (T > 4, single puzzle): the canonical position
+// word -- ordered goal: the position bytes as they are; set goal: the bytes sorted ascending
+// (tiles are interchangeable); bits 32..62: puzzle id (T <= 4); bit 63: "this successor meets
+// the goal" (carried through the exchange, ignored by dedup).  TS_BFS_NONE (all ones) marks a
+// move that changed nothing.
+//
+// Kernels:  bfs_seed (initial keys), K4 bfs_expand (frontier x 4 moves -> successor keys),
+// bfs_partition_count / bfs_partition_scatter (bucket successors by owner rank =
+// hash(key) % n_ranks, ahead of the NCCL all-to-all done by the Python driver), K5
+// bfs_hash_insert (open-addressing visited table, atomicCAS; emits the new keys = next
+// frontier).
+#include "ts_common.cuh"
+#include "../../include/tiler_slider.h"
+
+namespace ts {
+
+constexpr uint64_t BFS_NONE = ~0ull;
+constexpr uint64_t BFS_WON_BIT = 1ull << 63;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// element `idx` of a plane-layout board buffer as a 64-bit board
+template <int NB> __device__ __forceinline__ uint64_t load_board_elem(const uint8_t* base, size_t cap, size_t idx) {
+    uint64_t b = 0;
+    static_for<0, plane_count(NB)>([&](auto I) {
+        constexpr int k = decltype(I)::value;
+        constexpr int w = plane_width(NB, k), off = plane_offset(NB, k);
+        const uint8_t* p = base + (size_t)off * cap + idx * w;
+        uint64_t v;
+        if constexpr (w == 8) v = *reinterpret_cast<const uint64_t*>(p);
+        else if constexpr (w == 4) v = *reinterpret_cast<const uint32_t*>(p);
+        else if constexpr (w == 2) v = *reinterpret_cast<const uint16_t*>(p);
+        else v = *p;
+        b |= v << (8 * off);
+    });
+    return b;
+}
+
+// sort the T position bytes ascending (odd-even transposition network; T <= 8)
+template <int T> __device__ __forceinline__ void sort_bytes(uint32_t (&q)[(T + 3) / 4]) {
+    uint32_t b[T];
+    static_for<0, T>([&](auto I) { constexpr int i = decltype(I)::value; b[i] = byte_of<i % 4>(q[i / 4]); });
+#pragma unroll
+    for (int round = 0; round < T; ++round)
+#pragma unroll
+        for (int i = round & 1; i + 1 < T; i += 2) {
+            const uint32_t lo = min(b[i], b[i + 1]), hi = max(b[i], b[i + 1]);
+            b[i] = lo; b[i + 1] = hi;
+        }
+#pragma unroll
+    for (int w = 0; w < (T + 3) / 4; ++w) q[w] = 0;
+    static_for<0, T>([&](auto I) { constexpr int i = decltype(I)::value; q[i / 4] |= b[i] << (8 * (i % 4)); });
+}
+
+template <int T> __device__ __forceinline__ uint64_t make_key(const uint32_t (&q)[(T + 3) / 4], uint64_t pid) {
+    if constexpr (T <= 4) return (uint64_t)q[0] | (pid << 32);
+    else return (uint64_t)q[0] | ((uint64_t)q[1] << 32);
+}
+template <int T> __device__ __forceinline__ void split_key(uint64_t key, uint32_t (&q)[(T + 3) / 4], uint64_t& pid) {
+    q[0] = (uint32_t)key;
+    if constexpr (T <= 4) pid = (key >> 32) & 0x7FFFFFFFull;
+    else { q[1] = (uint32_t)(key >> 32) & 0x7FFFFFFFu; pid = 0; }
+}
+
+template <int S, int T>
+__global__ void __launch_bounds__(256) bfs_seed_kernel(const ts_bfs_args a) {
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_items) return;
+    uint32_t q[PR] = {};
+    const uint8_t* p = a.d_init + (size_t)i * PW;
+    static_for<0, T>([&](auto I) { constexpr int t = decltype(I)::value; q[t / 4] |= (uint32_t)p[t] << (8 * (t % 4)); });
+    if (a.goal_mode == TS_GOAL_SET) sort_bytes<T>(q);
+    a.d_out_keys[i] = make_key<T>(q, (uint64_t)i);
+}
+
+// K4: thread = one frontier state, four successors
+template <int S, int T>
+__global__ void __launch_bounds__(256) bfs_expand_kernel(const ts_bfs_args a) {
+    constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S);
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_items) return;
+    uint32_t q0[PR];
+    uint64_t pid;
+    split_key<T>(a.d_in_keys[i], q0, pid);
+    const size_t cap = (size_t)a.puzzle_capacity;
+    const uint64_t walls = load_board_elem<NB>(a.d_walls, cap, (size_t)pid);
+    uint64_t tboard = 0;
+    uint32_t tq[PR] = {};
+    if (a.goal_mode == TS_GOAL_SET) tboard = load_board_elem<NB>(a.d_targets_packed, cap, (size_t)pid);
+    else {
+        const uint8_t* p = a.d_targets_packed + (size_t)pid * PW;
+        static_for<0, T>([&](auto I) { constexpr int t = decltype(I)::value; tq[t / 4] |= (uint32_t)p[t] << (8 * (t % 4)); });
+    }
+#pragma unroll
+    for (uint32_t d = 0; d < 4; ++d) {
+        uint32_t q[PR];
+#pragma unroll
+        for (int w = 0; w < PR; ++w) q[w] = q0[w];
+        slide_env<S, T>(q, walls, d >> 1, (d & 1u) ^ 1u);
+        bool won = a.never_win == 0;
+        if (a.goal_mode == TS_GOAL_SET) {
+            won &= occupancy<S, T>(q) == tboard;
+            sort_bytes<T>(q);     // canonical form: tiles are interchangeable (state.py:185-186)
+        } else {
+#pragma unroll
+            for (int w = 0; w < PR; ++w) won &= q[w] == tq[w];
+        }
+        bool same = true;
+#pragma unroll
+        for (int w = 0; w < PR; ++w) same &= q[w] == q0[w];
+        uint64_t key = make_key<T>(q, pid) | (won ? BFS_WON_BIT : 0ull);
+        if (same && !won) key = BFS_NONE;
+        a.d_out_keys[4 * i + d] = key;
+    }
+}
+
+// owner rank of a key (won bit excluded)
+__device__ __forceinline__ uint32_t key_owner(uint64_t key, uint32_t n_ranks) {
+    return (uint32_t)((mix64(key & ~BFS_WON_BIT) >> 40) % n_ranks);
+}
+
+__global__ void __launch_bounds__(256) bfs_partition_count_kernel(const ts_bfs_args a) {
+    __shared__ unsigned int hist[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < a.n_items) {
+        const uint64_t key = a.d_in_keys[i];
+        if (key != BFS_NONE) atomicAdd(&hist[key_owner(key, (uint32_t)a.n_ranks)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.n_ranks && hist[threadIdx.x]) atomicAdd((unsigned long long*)&a.d_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// d_counts holds, on entry, the write cursor (= exclusive prefix offset) of every owner bucket
+__global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs_args a) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_items) return;
+    const uint64_t key = a.d_in_keys[i];
+    if (key == BFS_NONE) return;
+    const unsigned long long slot = atomicAdd((unsigned long long*)&a.d_counts[key_owner(key, (uint32_t)a.n_ranks)], 1ull);
+    a.d_out_keys[slot] = key;
+}
+
+// K5: insert keys into the open-addressing visited table (EMPTY = all ones).  New keys are
+// appended to d_out_keys through the cursor d_counts[0]; d_counts[1] counts won successors seen,
+// d_counts[2] is set when the table is full.
+__global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args a) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_items) return;
+    const uint64_t raw = a.d_in_keys[i];
+    if (raw == BFS_NONE) return;
+    const uint64_t key = raw & ~BFS_WON_BIT;
+    if (raw & BFS_WON_BIT) atomicAdd((unsigned long long*)&a.d_counts[1], 1ull);
+    const uint64_t mask = (uint64_t)a.table_capacity - 1;
+    uint64_t slot = mix64(key) & mask;
+    for (int64_t probe = 0; probe < a.table_capacity; ++probe) {
+        const unsigned long long old = atomicCAS((unsigned long long*)&a.d_table[slot], (unsigned long long)BFS_NONE, (unsigned long long)key);
+        if (old == BFS_NONE) {
+            const unsigned long long pos = atomicAdd((unsigned long long*)&a.d_counts[0], 1ull);
+            if ((int64_t)pos < a.out_capacity) a.d_out_keys[pos] = raw;
+            else a.d_counts[2] = 1;
+            return;
+        }
+        if (old == key) return;
+        slot = (slot + 1) & mask;
+    }
+    a.d_counts[2] = 1;
+}
+
+template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n_items + 255) / 256);
+#define TS_BFS_CASE(T)                                                                  \
+    case T:                                                                             \
+        if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
+        else bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);                        \
+        break;
+    switch (a.n_tiles) {
+        TS_BFS_CASE(1) TS_BFS_CASE(2) TS_BFS_CASE(3) TS_BFS_CASE(4)
+        TS_BFS_CASE(5) TS_BFS_CASE(6) TS_BFS_CASE(7) TS_BFS_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef TS_BFS_CASE
+    return cudaGetLastError();
+}
+
+static cudaError_t bfs_dispatch(int op, const ts_bfs_args& a, cudaStream_t st) {
+    switch (a.size) {
+        case 1: return bfs_dispatch_T<1>(op, a, st);
+        case 2: return bfs_dispatch_T<2>(op, a, st);
+        case 3: return bfs_dispatch_T<3>(op, a, st);
+        case 4: return bfs_dispatch_T<4>(op, a, st);
+        case 5: return bfs_dispatch_T<5>(op, a, st);
+        case 6: return bfs_dispatch_T<6>(op, a, st);
+        case 7: return bfs_dispatch_T<7>(op, a, st);
+        case 8: return bfs_dispatch_T<8>(op, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+static int bfs_check(const ts_bfs_args* a, bool needs_shape) {
+    if (!a) return TS_E_NULL_POINTER;
+    if (a->n_items < 0) return TS_E_BAD_RANGE;
+    if (needs_shape) {
+        if (a->size < 1 || a->size > 8) return TS_E_UNSUPPORTED;       // bitboard classes only
+        if (a->n_tiles < 1 || a->n_tiles > MAX_TILES) return TS_E_BAD_TILES;
+        if (a->puzzle_capacity <= 0 || a->puzzle_capacity % CAP_ALIGN) return TS_E_BAD_CAPACITY;
+        if (a->n_tiles > 4 && a->puzzle_capacity > CAP_ALIGN) return TS_E_UNSUPPORTED;   // T > 4: single puzzle, no id bits
+    }
+    return 0;
+}
+
+extern "C" {
+
+int ts_bfs_seed(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (!a->d_init || !a->d_out_keys) return TS_E_NULL_POINTER;
+    if (a->n_items == 0) return 0;
+    return (int)bfs_dispatch(0, *a, (cudaStream_t)stream);
+}
+
+int ts_bfs_expand(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_out_keys) return TS_E_NULL_POINTER;
+    if (a->n_items == 0) return 0;
+    return (int)bfs_dispatch(1, *a, (cudaStream_t)stream);
+}
+
+int ts_bfs_partition_count(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, false)) return rc;
+    if (!a->d_in_keys || !a->d_counts) return TS_E_NULL_POINTER;
+    if (a->n_ranks < 1 || a->n_ranks > 64) return TS_E_BAD_ARGUMENT;
+    if (a->n_items == 0) return 0;
+    bfs_partition_count_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+int ts_bfs_partition_scatter(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, false)) return rc;
+    if (!a->d_in_keys || !a->d_counts || !a->d_out_keys) return TS_E_NULL_POINTER;
+    if (a->n_ranks < 1 || a->n_ranks > 64) return TS_E_BAD_ARGUMENT;
+    if (a->n_items == 0) return 0;
+    bfs_partition_scatter_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+int ts_bfs_hash_insert(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, false)) return rc;
+    if (!a->d_in_keys || !a->d_counts || !a->d_out_keys || !a->d_table) return TS_E_NULL_POINTER;
+    if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
+    if (a->n_items == 0) return 0;
+    bfs_hash_insert_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
