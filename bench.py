@@ -41,6 +41,9 @@ PUZZLE_SEED, ACTION_SEED = 1002, 2002
 ALGO_BYTES = 3 * T + (S * S + 7) // 8 + 8      # 25 B per env-step
 METRIC = "env-steps/sec at 1/2/4/8 B200 and % HBM roofline vs reference CPU step loop"
 UNIT = "env-steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default
+# size, from the committed `ncu --set full` capture (profiles/r1_v3_step_kernel_full_raw.csv)
+NCU_TRAFFIC_BYTES = {"c3": 268.447488e6 + 135.936256e6}
 N_ACTION_ROWS = 8                               # distinct pre-generated action vectors, cycled
 
 
@@ -322,6 +325,8 @@ def main() -> int:
     select_config(args.config)
     if args.envs is None:
         args.envs = ENVS_PER_GPU
+    if args.traffic_bytes is None and args.envs == ENVS_PER_GPU:
+        args.traffic_bytes = NCU_TRAFFIC_BYTES.get(args.config)
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
