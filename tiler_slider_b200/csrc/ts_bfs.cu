@@ -231,41 +231,41 @@ extern "C" {
 
 int ts_bfs_seed(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, true)) return rc;
-    if (!a->d_init || !a->d_out_keys) return TS_E_NULL_POINTER;
     if (a->n_items == 0) return 0;
+    if (!a->d_init || !a->d_out_keys) return TS_E_NULL_POINTER;
     return (int)bfs_dispatch(0, *a, (cudaStream_t)stream);
 }
 
 int ts_bfs_expand(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, true)) return rc;
+    if (a->n_items == 0) return 0;   // an empty local frontier is normal on a multi-rank search
     if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_out_keys) return TS_E_NULL_POINTER;
-    if (a->n_items == 0) return 0;
     return (int)bfs_dispatch(1, *a, (cudaStream_t)stream);
 }
 
 int ts_bfs_partition_count(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, false)) return rc;
-    if (!a->d_in_keys || !a->d_counts) return TS_E_NULL_POINTER;
     if (a->n_ranks < 1 || a->n_ranks > 64) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
+    if (!a->d_in_keys || !a->d_counts) return TS_E_NULL_POINTER;
     bfs_partition_count_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
 int ts_bfs_partition_scatter(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, false)) return rc;
-    if (!a->d_in_keys || !a->d_counts || !a->d_out_keys) return TS_E_NULL_POINTER;
     if (a->n_ranks < 1 || a->n_ranks > 64) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
+    if (!a->d_in_keys || !a->d_counts) return TS_E_NULL_POINTER;   // d_out_keys may be NULL when every key is NONE
     bfs_partition_scatter_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
 int ts_bfs_hash_insert(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, false)) return rc;
-    if (!a->d_in_keys || !a->d_counts || !a->d_out_keys || !a->d_table) return TS_E_NULL_POINTER;
     if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
+    if (!a->d_in_keys || !a->d_counts || !a->d_out_keys || !a->d_table) return TS_E_NULL_POINTER;
     bfs_hash_insert_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
