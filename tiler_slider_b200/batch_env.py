@@ -194,8 +194,8 @@ class BatchedTilerSliderEnv:
     def _stage_actions(self, actions) -> int:
         n = self.n_envs
         if isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.is_cuda \
-                and actions.device == self.device and actions.is_contiguous() and actions.numel() >= _round_up(n, 4) \
-                and actions.data_ptr() % 16 == 0:
+                and actions.device == self.device and actions.is_contiguous() and actions.numel() >= self.capacity \
+                and actions.data_ptr() % 16 == 0:   # kernels may read (and ignore) the padding envs up to capacity
             return actions.data_ptr()
         a = torch.as_tensor(actions)
         if a.numel() != n:
