@@ -278,6 +278,68 @@ def test_pipelined_kernel_matches_direct_kernel_and_oracle(ts, S, T, W, multi, a
         assert np.array_equal(r[:n_chk].cpu().numpy(), want["reward"][k])
 
 
+def test_full_size_properties(ts):
+    """BASELINE config 3 at its full size (16,777,216 envs, 6x6, 4 coloured tiles, 8 walls):
+    size-independent properties of the move --
+      * well-formedness is preserved: tiles stay in bounds, distinct, never on a wall;
+      * idempotence: repeating the same action moves nothing (every env reports invalid_move);
+      * reversal symmetry: after UP, DOWN brings every tile to the cell a single DOWN would not
+        pass -- checked as 'DOWN after UP == DOWN after (UP, DOWN, UP, DOWN)' (a slide to the far
+        side forgets the history along that axis);
+      * determinism: two independently built envs end with the same checksum;
+    plus the first 4,096 envs against the oracle."""
+    S, T, W, N = 6, 4, 8, 16_777_216
+    env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=1002, max_steps=255, auto_reset=False)
+    walls = env.blocked_cells()
+
+    def check_well_formed():
+        p = env.positions().to(torch.int64)
+        cell = p[..., 0] * S + p[..., 1]
+        assert int(p.max()) < S and int(p.min()) >= 0
+        assert not bool(walls.gather(1, cell).any())
+        srt = cell.sort(dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())
+
+    def act(d):
+        return torch.full((env.capacity,), d, dtype=torch.uint8, device="cuda")
+
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    n_chk = 4096
+    blocked = walls[:n_chk].cpu().numpy().astype(np.uint8)
+    tiles0 = env.positions()[:n_chk].cpu().numpy()
+    targets = env.target_positions()[:n_chk].cpu().numpy()
+    rand_actions = torch.randint(0, 4, (6, env.capacity), dtype=torch.uint8, device="cuda", generator=gen)
+    for k in range(6):
+        env.step(rand_actions[k])
+    check_well_formed()
+    want = orc.rollout(S, True, blocked, tiles0, targets, rand_actions[:, :n_chk].cpu().numpy(), max_steps=255)
+    assert np.array_equal(env.positions()[:n_chk].cpu().numpy(), want["final_pos"])
+    live = (env.flags & F_DONE) == 0
+    for d in range(4):
+        env.step(act(d))
+        first = env.pos.clone()
+        env.step(act(d))                                   # same action again: nothing may move
+        still_live = live & ((env.flags & F_STALE) == 0)
+        assert torch.equal(env.pos, first)
+        assert bool(((env.flags & F_INVALID) != 0)[still_live].all())
+        live = (env.flags & F_DONE) == 0
+    check_well_formed()
+    env.reset()
+    env.step(act(0)); env.step(act(1))
+    once = env.pos.clone()
+    env.step(act(0)); env.step(act(1))
+    assert torch.equal(env.pos[live_after_reset(env)], once[live_after_reset(env)])
+    checksum = int((env.pos.to(torch.int64) * torch.arange(1, 5, device="cuda")).sum())
+    env2 = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=1002, max_steps=255, auto_reset=False)
+    for d in (0, 1, 0, 1):
+        env2.step(act(d))
+    assert int((env2.pos.to(torch.int64) * torch.arange(1, 5, device="cuda")).sum()) == checksum
+
+
+def live_after_reset(env):
+    return (env.flags & (F_DONE | F_STALE)) == 0
+
+
 def test_step_host_matches_step(ts):
     S, T, W, N = 6, 4, 8, 50_000
     a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=9, auto_reset=True)

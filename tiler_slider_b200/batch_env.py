@@ -219,8 +219,13 @@ class BatchedTilerSliderEnv:
             n = self.n_envs
             self._cached_out = (self._pos[:n], self._reward[:n], self._done[:n].view(torch.bool))
         a.d_actions = ptr
-        with torch.cuda.device(self.device):
-            check(self._lib.ts_step(C.byref(a), self._stream()), "ts_step")
+        if torch.cuda.current_device() == self.device.index:      # skip the device-guard round trip (host-bound small batches)
+            rc = self._lib.ts_step(C.byref(a), torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc = self._lib.ts_step(C.byref(a), self._stream())
+        if rc:
+            check(rc, "ts_step")
         return self._cached_out
 
     def raw_move(self, actions) -> torch.Tensor:
