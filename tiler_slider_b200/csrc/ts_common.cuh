@@ -18,7 +18,7 @@
 //                   goal) use the same stride without sentinels.
 //   S = 7, 8 (compact boards): BS = S, PS = 16, no sentinels.
 //   S >= 9 (wide boards): PS = 16; walls are four pre-oriented 32-byte sectors per env
-//                   (walls[env][action][line] u16), the set-goal target board one sector
+//                   (walls[action][env][line] u16), the set-goal target board one sector
 //                   (tboard[env][row] u16); see ts_wide.cu.
 //   capacity        allocation stride in envs, a multiple of 128 so that every plane start and
 //                   every 4-env group is 16-byte aligned

@@ -6,14 +6,17 @@
 // 119-143), reset (environment.py:89-97), get_valid_moves (environment.py:149-171).
 //
 // A wide board does not fit a 64-bit word, so the bitboard tricks of ts_common.cuh do not
-// apply.  Layout (env-major, one 32-byte sector per orientation):
-//   walls[env][a][line]  u16, a = action (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT): the board
+// apply.  Layout (one 32-byte sector per env and orientation, orientation-major planes):
+//   walls[a][env][line]  u16, a = action (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT): the board
 //                        pre-oriented for that move -- `line` is the row (LEFT/RIGHT) or the
-//                        column (UP/DOWN) and bit o is the o-th cell of that line counted
-//                        TOWARD the move direction's far end reversed, i.e. a slide always
-//                        goes toward higher bits.  The walls are static, so the four
+//                        column (UP/DOWN) and bit o is the cell at distance o from the end of
+//                        the line the move goes AWAY from, i.e. a slide always goes toward
+//                        higher bits.  The walls are static, so the four
 //                        orientations are written once by ts_encode / ts_synth; a step reads
 //                        exactly ONE 32-byte sector of them (select-source load), never all.
+//                        (Planes, not [env][a]: ncu showed DRAM fetching the whole 128-byte
+//                        line around a sector, i.e. all four orientations of the env.)
+//                        For S <= 15 bit S of every line is stored as 1 (edge sentinel).
 //   tboard[env][row]     u16 target cells (set goal only)
 //   position byte        row*16 + col
 // Thread = one env.  The 16 line words of the chosen orientation and the occupancy lines
@@ -49,10 +52,11 @@ __device__ __forceinline__ uint32_t half_of(uint32_t word, uint32_t half) {
     return __byte_perm(word, 0, 0x4410u + half * 0x22u);   // half ? word >> 16 : word & 0xffff
 }
 
-// One slide of all T tiles of the calling thread's env.  `board` = the 32-byte orientation
-// sector for `action`.  q: position bytes (row*16+col), updated in place.
+// One slide of all T tiles of the calling thread's env, S == 16 (no room for a stored sentinel in
+// a 16-bit line: lines are extracted and the edge bit is OR-ed in).  `board` = the 32-byte
+// orientation sector for `action`.  q: position bytes (row*16+col), updated in place.
 template <int T>
-__device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
+__device__ __forceinline__ void slide_wide16(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
     constexpr int PR = (T + 3) / 4;
     const int tid = threadIdx.x;
     const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
@@ -98,6 +102,57 @@ __device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) /
     if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
 }
 
+// One slide, 9 <= S <= 15: every stored line word carries its edge sentinel at bit S, so a pair
+// word (two 16-bit lines) is used as it is -- shifting it right by 16*(line&1) + offset + 1
+// leaves exactly the cells past the tile, and the scan stops at the line's own sentinel before
+// it can reach the neighbouring line's bits.  That shift amount is the low 5 bits of the byte
+// (line<<4 | offset), plus one.
+template <int T>
+__device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
+    constexpr int PR = (T + 3) / 4;
+    const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
+    const uint4 b0 = __ldg(board), b1 = __ldg(board + 1);
+    uint32_t* wcol = &sm.w[0][threadIdx.x];     // this thread's column: pair k at wcol[k * WIDE_THREADS]
+    uint32_t* ocol = &sm.o[0][threadIdx.x];
+    wcol[0 * WIDE_THREADS] = b0.x; wcol[1 * WIDE_THREADS] = b0.y; wcol[2 * WIDE_THREADS] = b0.z; wcol[3 * WIDE_THREADS] = b0.w;
+    wcol[4 * WIDE_THREADS] = b1.x; wcol[5 * WIDE_THREADS] = b1.y; wcol[6 * WIDE_THREADS] = b1.z; wcol[7 * WIDE_THREADS] = b1.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ocol[k * WIDE_THREADS] = 0;
+
+    // line / offset nibbles of every tile; offsets flipped for UP/LEFT with one multiply-add
+    const uint32_t fm = 1u - 2u * f, fk = f * (0x01010101u * (uint32_t)(S - 1));
+    uint32_t LN[PR], OF[PR], B[PR], ACC[PR];
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        const uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu, lo = q[w] & 0x0F0F0F0Fu;   // rows, cols
+        LN[w] = h ? hi : lo;
+        OF[w] = (h ? lo : hi) * fm + fk;
+        B[w] = LN[w] * 16u + OF[w];
+        ACC[w] = 0;
+    }
+    uint32_t pofs[T], sh[T];
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t b = byte_of<i % 4>(B[i / 4]);
+        pofs[i] = (b >> 5) * WIDE_THREADS;           // pair index = line >> 1
+        sh[i] = b & 31u;                             // 16*(line&1) + offset
+        ocol[pofs[i]] |= 1u << sh[i];
+    });
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t x = (wcol[pofs[i]] >> sh[i]) >> 1;     // cells past the tile, sentinel included
+        const uint32_t y = (ocol[pofs[i]] >> sh[i]) >> 1;
+        const uint32_t run = (x - 1u) & ~x;                   // cells before the first wall / the edge
+        ACC[i / 4] = mad_u32((uint32_t)__popc(run & ~y), 1u << (8 * (i % 4)), ACC[i / 4]);
+    });
+#pragma unroll
+    for (int w = 0; w < PR; ++w) {
+        const uint32_t ofn = (OF[w] + ACC[w]) * fm + fk;      // new offset, un-flipped
+        q[w] = (h ? LN[w] : ofn) * 16u + (h ? ofn : LN[w]);
+    }
+    if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
+}
+
 // set goal: every tile stands on a target cell (ts_encode guarantees the target board is empty
 // unless it has exactly T distinct cells, so this is set equality; state.py:185-186)
 template <int T>
@@ -128,7 +183,8 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_co
                                         : reinterpret_cast<const uint32_t*>(a.d_step_count)[env];
     const bool stale = !a.auto_reset && (a.d_flags[env] & F_DONE);
 
-    slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + (env * 4 + action) * 2, a.size, action);
+    if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)action * (size_t)a.capacity + env) * 2, a.size, action);
+    else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)action * (size_t)a.capacity + env) * 2, a.size, action);
 
     bool moved = false, won = a.never_win == 0;
 #pragma unroll
@@ -183,7 +239,8 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_c
         uint32_t q[PR];
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
-        slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + (env * 4 + d) * 2, a.size, d);
+        if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)d * (size_t)a.capacity + env) * 2, a.size, d);
+        else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)d * (size_t)a.capacity + env) * 2, a.size, d);
         bool moved = false;
 #pragma unroll
         for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
