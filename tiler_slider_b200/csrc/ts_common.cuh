@@ -237,17 +237,30 @@ template <int S> struct Padded {
     static constexpr uint64_t SENT = sentinel_cols() | (~0ull << NBITS);   // what a stored wall board has set
 };
 
-// h = 1 for LEFT/RIGHT, f = 1 for UP/LEFT (the directions that need the 180-degree rotation)
+// Per-direction constants of the padded slide.  st: bit stride of the move; lm: line mask;
+// fm / fk: positions are rotated as p' = p * fm + fk (fm = -1, fk = KREV per byte for UP/LEFT).
+struct DirParams {
+    uint32_t st, lm, fm, fk;
+};
+// h = 1 for LEFT/RIGHT, f = 1 for UP/LEFT (the directions that need the 180-degree rotation).
+// Integer multiply-adds, not selects: the step is bound by instruction issue on the ALU pipe
+// (LOP3/SHF/SEL/PRMT), IMAD runs on the FMA pipe.
+template <int S> __device__ __forceinline__ DirParams dir_params(uint32_t h, uint32_t f) {
+    using PD = Padded<S>;
+    DirParams d;
+    d.st = (uint32_t)PD::BS - h * (uint32_t)(PD::BS - 1);   // h ? 1 : BS
+    d.lm = PD::COL + h * ~PD::COL;                           // h ? ~0 : COL
+    d.fm = 1u - 2u * f;                                      // f ? -1 : +1
+    d.fk = f * PD::KREV4;                                    // f ? KREV4 : 0
+    return d;
+}
+
 template <int S, int T>
-__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t h, uint32_t f) {
+__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, const DirParams& dp) {
     using PD = Padded<S>;
     constexpr int PR = (T + 3) / 4;
-    // Direction parameters as integer multiply-adds: the kernel is bound by the ALU pipe
-    // (LOP3/SHF/SEL/PRMT), so selects are moved to the FMA pipe (IMAD) wherever possible.
-    const uint32_t st = (uint32_t)PD::BS - h * (uint32_t)(PD::BS - 1);   // h ? 1 : BS
-    const uint32_t lm = PD::COL + h * ~PD::COL;                           // h ? ~0 : COL
-    const uint32_t fm = 1u - 2u * f;                                      // f ? -1 : +1
-    const uint32_t fk = f * PD::KREV4;                                    // f ? KREV4 : 0
+    const uint32_t st = dp.st, lm = dp.lm, fm = dp.fm, fk = dp.fk;
+    const bool f = (int32_t)fm < 0;
     // bytes past the stored board read as zero in the plane layout: (re)assert the sentinels
     const uint64_t w0 = walls | (~0ull << PD::NBITS);
     const uint64_t wr = (__brevll(walls) >> (63 - PD::KREV)) | PD::TAIL;
@@ -376,7 +389,7 @@ __device__ __forceinline__ uint64_t occupancy_compact(const uint32_t (&q)[(T + 3
 // (state.py:31-34).
 template <int S, int T>
 __device__ __forceinline__ void slide_env(uint32_t (&q)[(T + 3) / 4], uint64_t walls, uint32_t h, uint32_t f) {
-    if constexpr (padded_board(S)) slide_padded<S, T>(q, walls, h, f);
+    if constexpr (padded_board(S)) slide_padded<S, T>(q, walls, dir_params<S>(h, f));
     else slide_compact<S, T>(q, walls, h, f);
 }
 // the h / f bits of the four actions of a thread's envs, one per byte (SWAR decode)

@@ -57,8 +57,11 @@ struct StepInputs {
 // The fused step of one 4-env group: slide, goal, bookkeeping, reward, auto-reset, stores.
 // AR: auto-reset on (flags are write-only) / off (done envs are frozen and report STALE)
 // CW: bytes of the step counter (1: SWAR bookkeeping, 4: per-env)
+// dir_tab: the four DirParams (one per action) in shared memory, padded boards only; one
+// conflict-free LDS.128 per env replaces the per-env decode of the action bits.
 template <int S, int T, int GOAL, bool AR, int CW>
-__device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, StepInputs<S, T, GOAL, CW>& in) {
+__device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, StepInputs<S, T, GOAL, CW>& in,
+                                           const uint4* dir_tab) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S);
     constexpr int NWORDS = (NB + 3) / 4;
     const size_t e0 = (size_t)g * GROUP;
@@ -86,7 +89,12 @@ __device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, St
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
         in.walls.get(e, bw);
-        slide_env<S, T>(q, board64(bw), (h4 >> (8 * e)) & 0xFFu, (f4 >> (8 * e)) & 0xFFu);
+        if constexpr (padded_board(S)) {
+            const uint4 d = dir_tab[(in.act4 >> (8 * e)) & 3u];
+            slide_padded<S, T>(q, board64(bw), DirParams{d.x, d.y, d.z, d.w});
+        } else {
+            slide_env<S, T>(q, board64(bw), (h4 >> (8 * e)) & 0xFFu, (f4 >> (8 * e)) & 0xFFu);
+        }
 
         bool moved = false;
 #pragma unroll
@@ -171,10 +179,23 @@ __device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, St
     if (a.d_flags) __stcs(reinterpret_cast<unsigned int*>(a.d_flags + e0), flags4);
 }
 
+// fill the per-block table of direction parameters (threads 0..3) -- call before any early return
+template <int S> __device__ __forceinline__ void fill_dir_tab(uint4* dir_tab) {
+    if constexpr (padded_board(S)) {
+        if (threadIdx.x < 4) {
+            const DirParams d = dir_params<S>(threadIdx.x >> 1, ~threadIdx.x & 1u);
+            dir_tab[threadIdx.x] = make_uint4(d.st, d.lm, d.fm, d.fk);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- direct kernel: every thread loads its own group straight from global memory --------------
 template <int S, int T, int GOAL, bool AR, int CW>
 __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR, CW>())) step_kernel(const __grid_constant__ ts_step_args a) {
     constexpr int PW = pos_bytes(T);
+    __shared__ uint4 dir_tab[4];
+    fill_dir_tab<S>(dir_tab);
     // 32-bit group index: every address below is base + g * constant, one IMAD.WIDE each
     // (ts_step rejects capacities of 2^32 groups or more)
     const uint32_t n_groups = (uint32_t)((a.n_envs + GROUP - 1) / GROUP);
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     }
     in.prev_flags = 0;
     if constexpr (!AR) in.prev_flags = __ldcs(reinterpret_cast<const unsigned int*>(a.d_flags + e0));
-    step_group<S, T, GOAL, AR, CW>(a, g, in);
+    step_group<S, T, GOAL, AR, CW>(a, g, in, dir_tab);
 }
 
 // ---- pipelined kernel: persistent CTAs, bulk-async (TMA 1-D) staging through shared memory -----
@@ -306,6 +327,8 @@ __global__ void __launch_bounds__(PIPE_THREADS) step_kernel_pipe(const __grid_co
     constexpr int PW = L::PW, NB = L::NB;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[PIPE_STAGES];
+    __shared__ uint4 dir_tab[4];
+    fill_dir_tab<S>(dir_tab);
 
     const uint32_t tid = threadIdx.x;
     const size_t cap = (size_t)a.capacity;
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(PIPE_THREADS) step_kernel_pipe(const __grid_co
                 issue(next, stage);
             }
         }
-        if (active) step_group<S, T, GOAL, AR, 1>(a, g_first + tile * PIPE_THREADS + tid, in);
+        if (active) step_group<S, T, GOAL, AR, 1>(a, g_first + tile * PIPE_THREADS + tid, in, dir_tab);
     }
 }
 
