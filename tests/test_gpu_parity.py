@@ -340,6 +340,22 @@ def live_after_reset(env):
     return (env.flags & (F_DONE | F_STALE)) == 0
 
 
+def test_cuda_graph_replay_matches_eager(ts):
+    S, T, W, N, R = 5, 1, 5, 10_000, 8
+    a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, False, seed=4, auto_reset=True)
+    b = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, False, seed=4, auto_reset=True)
+    rows = torch.randint(0, 4, (R, a.capacity), dtype=torch.uint8, device="cuda")
+    graph = a.capture_steps(rows)
+    a.reset()
+    for _ in range(3):
+        graph.replay()
+        for k in range(R):
+            b.step(rows[k])
+        torch.cuda.synchronize()
+        assert torch.equal(a.pos, b.pos) and torch.equal(a.step_count, b.step_count)
+        assert torch.equal(a.reward, b.reward) and torch.equal(a.flags, b.flags)
+
+
 def test_step_host_matches_step(ts):
     S, T, W, N = 6, 4, 8, 50_000
     a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=9, auto_reset=True)

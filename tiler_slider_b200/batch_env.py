@@ -228,6 +228,28 @@ class BatchedTilerSliderEnv:
             check(rc, "ts_step")
         return self._cached_out
 
+    def capture_steps(self, action_rows: torch.Tensor) -> "torch.cuda.CUDAGraph":
+        """Capture `len(action_rows)` consecutive steps (row k = the actions of step k, uint8
+        [R, capacity] on this device) into one CUDA graph; `graph.replay()` then advances the
+        batch R steps with a single host call.  For launch-bound batches (about 1M envs and
+        below) the per-step host cost of Python + ctypes otherwise exceeds the kernel time."""
+        self._require_loaded()
+        if action_rows.dtype != torch.uint8 or action_rows.device != self.device or action_rows.dim() != 2 \
+                or action_rows.shape[1] < self.capacity or not action_rows.is_contiguous():
+            raise ValueError("action_rows must be a contiguous uint8 [R, >= capacity] tensor on the env's device")
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.step(action_rows[0])                      # warm-up outside capture (lazy init)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.reset()
+            with torch.cuda.graph(graph):
+                for k in range(action_rows.shape[0]):
+                    self.step(action_rows[k])
+        return graph
+
     def raw_move(self, actions) -> torch.Tensor:
         """GameState.move (state.py:120-170) without episode bookkeeping: slides the tiles and
         returns the flags (WON / INVALID bits); step_count, done state and `flags` of the
