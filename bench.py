@@ -278,6 +278,19 @@ def run_ours(args) -> int:
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_local * world * e2e_steps / float(e2e_s.item())
+    # compact variant: only the status byte travels back (done = bit 0, reward = f(WON, INVALID))
+    h_flags = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        env.step_host(h_act, h_flags=h_flags)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        env.step_host(h_act, h_flags=h_flags)
+    barrier()
+    e2c_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2c_s, op=dist.ReduceOp.MAX)
+    e2e_compact = n_local * world * e2e_steps / float(e2c_s.item())
 
     if rank == 0:
         peaks = {}
@@ -299,7 +312,10 @@ def run_ours(args) -> int:
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * world,
                         "d2h_bytes_per_step": 5 * n_local * world, "steps": e2e_steps,
-                        "path": "BatchedTilerSliderEnv.step_host -> ts_step_host (pinned host actions in, reward f32 + done u8 out)"},
+                        "path": "BatchedTilerSliderEnv.step_host -> ts_step_host (pinned host actions in, reward f32 + done u8 out)",
+                        "compact_variant": {"value": e2e_compact, "d2h_bytes_per_step": n_local * world,
+                                            "what": "same call, only the 1-byte status word downloaded (done = bit 0, "
+                                                    "reward = function of the WON / INVALID bits)"}},
                 "gpu_launches": args.steps, "clocks": clocks, "cuda_graph": bool(args.graph),
                 "wins_in_last_step": int(wins.item())}
         if world == 1 and not args.no_cpu:

@@ -241,12 +241,15 @@ int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
  * h_actions (pinned) -> device, ts_step, reward/done -> h_reward/h_done (pinned), pipelined in
  * chunks over the context's streams; returns after everything has landed.
  * a->d_actions/d_reward/d_done must still point at device staging of n_envs elements.
+ * h_flags (optional, pinned): also download the TS_F_* status byte.  With h_reward = h_done =
+ * NULL only that byte comes back (1 instead of 5 bytes per env over PCIe): it encodes done (bit
+ * 0) and, since reward is a function of WON / INVALID, the reward.
  * ------------------------------------------------------------------------------------- */
 typedef struct ts_host_ctx ts_host_ctx;
 int ts_host_ctx_create(ts_host_ctx **out, int n_streams);
 int ts_host_ctx_destroy(ts_host_ctx *ctx);
 int ts_step_host(ts_host_ctx *ctx, const ts_step_args *a, const uint8_t *h_actions, float *h_reward,
-                 uint8_t *h_done, int64_t chunk_envs);
+                 uint8_t *h_done, uint8_t *h_flags, int64_t chunk_envs);
 
 #ifdef __cplusplus
 }

@@ -146,15 +146,16 @@ def test_set_goal_with_duplicate_and_missing_targets(ts):
     assert want["flags"][0, 0] & F_WON and not (want["flags"][:, 1] & F_WON).any()
 
 
-def test_ordered_goal_length_mismatch_never_wins(ts):
+def test_ordered_goal_length_mismatch_is_rejected(ts):
+    """state.py:183-184: with a different number of targets an ordered goal can never be met; the
+    packed layout has no room for such targets, so the batch is refused (no host fallback)."""
     blocked = np.zeros((1, 9), np.uint8)
     tiles = np.array([[[0, 0]]], np.uint8)
     targets = np.array([[[0, 2], [2, 2]]], np.uint8)
-    acts = np.array([[3], [1]], np.uint8)
-    want = orc.rollout(3, True, blocked, tiles, targets, acts)
-    got = run_gpu(ts, 3, True, blocked, tiles, targets, acts, 100, False)
-    assert_same(got, want)
-    assert not (got["flags"] & F_WON).any()
+    with pytest.raises(ValueError, match="as many targets as tiles"):
+        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, tiles, targets, True)
+    with pytest.raises(ValueError):
+        ts.GameState(3, [], [], [(0, 0)], False)
 
 
 def test_observation_valid_moves_goal(ts):
@@ -370,6 +371,18 @@ def test_step_host_matches_step(ts):
         b.step_host(h_act, h_rew, h_done, chunk_envs=8192)
         assert torch.equal(a.pos, b.pos)
         assert torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done.bool())
+    c = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=9, auto_reset=True)
+    h_flags = torch.empty(N, dtype=torch.uint8).pin_memory()
+    lut = torch.tensor([c.rewards[1], 0, c.rewards[0], 0, c.rewards[2], 0, c.rewards[0], 0], dtype=torch.float32)
+    rng = np.random.default_rng(1)
+    for k in range(20):
+        h_act.copy_(torch.from_numpy(rng.integers(0, 4, N, dtype=np.uint8)))
+        c.step_host(h_act, h_flags=h_flags, chunk_envs=8192)
+    # after the same 20 action vectors the compact path is in the same state as the others, and
+    # its status byte reproduces done and reward
+    assert torch.equal(c.pos, a.pos)
+    assert torch.equal((h_flags & 1).bool(), h_done.bool())
+    assert torch.equal(lut[((h_flags >> 1) & 3).long() * 2], h_rew)
 
 
 def test_argument_errors(ts):

@@ -102,7 +102,7 @@ SYMBOLS = {
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "ts_host_ctx_destroy": (C.c_int, [_vp]),
-    "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _i64]),
+    "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _vp, _i64]),
 }
 
 

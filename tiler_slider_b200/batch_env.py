@@ -55,8 +55,11 @@ class BatchedTilerSliderEnv:
         self.n_targets = self.n_tiles if n_targets is None else int(n_targets)
         # T == 1 with one target: ordered and set equality coincide; use the cheaper compare
         self.goal_mode = GOAL_ORDERED if (self.multi_color or (self.n_tiles == 1 and self.n_targets == 1)) else GOAL_SET
-        # ordered list equality with a length mismatch is never true (state.py:183-184)
-        self.never_win = bool(self.multi_color and self.n_targets != self.n_tiles)
+        # ordered list equality with a length mismatch is never true (state.py:183-184): such a
+        # batch could never report a win and its targets do not fit the packed layout
+        if self.multi_color and self.n_targets != self.n_tiles:
+            raise ValueError("multi-colour batches need as many targets as tiles")
+        self.never_win = False
         self.max_steps = int(max_steps)
         self.auto_reset = bool(auto_reset)
         self.rewards = tuple(float(x) for x in rewards)
@@ -148,10 +151,6 @@ class BatchedTilerSliderEnv:
         t = tiles.to(dev, torch.uint8).contiguous()
         g = targets.to(dev, torch.uint8).contiguous()
         nt = g.shape[1]
-        if self.goal_mode == GOAL_ORDERED and nt != self.n_tiles:
-            # never_win batch: the packed targets are never compared; keep zeros
-            g = torch.zeros(self.n_envs, self.n_tiles, 2, dtype=torch.uint8, device=dev)
-            nt = self.n_tiles
         a = EncodeArgs(size=self.size, n_tiles=self.n_tiles, n_targets=nt, goal_mode=self.goal_mode,
                        first_env=0, n_envs=self.n_envs, capacity=self.capacity,
                        d_blocked=_ptr(b), d_tiles=_ptr(t), d_targets=_ptr(g) if nt else None,
@@ -269,14 +268,19 @@ class BatchedTilerSliderEnv:
         return self._scratch_flags[: self.n_envs]
 
     # ------------------------------------------------------------------ host-buffer path
-    def step_host(self, h_actions: torch.Tensor, h_reward: torch.Tensor, h_done: torch.Tensor,
-                  chunk_envs: int = 1 << 21, n_streams: int = 4) -> None:
+    def step_host(self, h_actions: torch.Tensor, h_reward: torch.Tensor | None = None, h_done: torch.Tensor | None = None,
+                  h_flags: torch.Tensor | None = None, chunk_envs: int = 1 << 21, n_streams: int = 4) -> None:
         """The same step driven from pinned HOST buffers (ts_step_host): uploads the actions,
-        runs K2 and downloads reward/done, pipelined in chunks; returns when done."""
+        runs K2 and downloads reward + done (and / or the status byte `flags`), pipelined in
+        chunks; returns when everything has landed.  With only `h_flags` given, 1 byte per env
+        comes back instead of 5: bit 0 is done, and the reward follows from the WON / INVALID
+        bits (`rewards`)."""
         self._require_loaded()
-        for t, dt in ((h_actions, torch.uint8), (h_reward, torch.float32), (h_done, torch.uint8)):
-            if t.is_cuda or t.dtype != dt or t.numel() < self.n_envs or not t.is_contiguous():
-                raise ValueError("step_host needs contiguous host tensors: uint8 actions, float32 reward, uint8 done")
+        if h_flags is None and (h_reward is None or h_done is None):
+            raise ValueError("step_host needs h_reward and h_done, or h_flags")
+        for t, dt in ((h_actions, torch.uint8), (h_reward, torch.float32), (h_done, torch.uint8), (h_flags, torch.uint8)):
+            if t is not None and (t.is_cuda or t.dtype != dt or t.numel() < self.n_envs or not t.is_contiguous()):
+                raise ValueError("step_host needs contiguous host tensors: uint8 actions, float32 reward, uint8 done / flags")
         if self._host_ctx is None:
             h = C.c_void_p()
             with torch.cuda.device(self.device):
@@ -285,8 +289,8 @@ class BatchedTilerSliderEnv:
         a = self._step_args(self._actions.data_ptr())
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()
-            check(self._lib.ts_step_host(self._host_ctx, C.byref(a), h_actions.data_ptr(), h_reward.data_ptr(),
-                                         h_done.data_ptr(), _round_up(chunk_envs, CAP_ALIGN)), "ts_step_host")
+            check(self._lib.ts_step_host(self._host_ctx, C.byref(a), h_actions.data_ptr(), _ptr(h_reward), _ptr(h_done),
+                                         _ptr(h_flags), _round_up(chunk_envs, CAP_ALIGN)), "ts_step_host")
 
     def __del__(self):
         h, self._host_ctx = getattr(self, "_host_ctx", None), None

@@ -41,9 +41,11 @@ int ts_host_ctx_destroy(ts_host_ctx* ctx) {
 }
 
 int ts_step_host(ts_host_ctx* ctx, const ts_step_args* a, const uint8_t* h_actions, float* h_reward,
-                 uint8_t* h_done, int64_t chunk_envs) {
-    if (!ctx || !a || !h_actions || !h_reward || !h_done) return TS_E_NULL_POINTER;
+                 uint8_t* h_done, uint8_t* h_flags, int64_t chunk_envs) {
+    if (!ctx || !a || !h_actions) return TS_E_NULL_POINTER;
+    if (!h_flags && (!h_reward || !h_done)) return TS_E_NULL_POINTER;   // need reward+done, or the flag byte
     if (!a->d_actions || !a->d_reward || !a->d_done) return TS_E_NULL_POINTER;
+    if (h_flags && !a->d_flags) return TS_E_NULL_POINTER;
     if (chunk_envs <= 0 || chunk_envs % ts::CAP_ALIGN != 0) return TS_E_BAD_ARGUMENT;
     const int ns = (int)ctx->streams.size();
     int rc = 0;
@@ -60,9 +62,12 @@ int ts_step_host(ts_host_ctx* ctx, const ts_step_args* a, const uint8_t* h_actio
         sub.n_envs = n;
         rc = ts_step(&sub, s);
         if (rc) break;
-        e = cudaMemcpyAsync(h_reward + off, a->d_reward + e0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess)
+        e = cudaSuccess;
+        if (h_reward) e = cudaMemcpyAsync(h_reward + off, a->d_reward + e0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && h_done)
             e = cudaMemcpyAsync(h_done + off, a->d_done + e0, (size_t)n, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && h_flags)
+            e = cudaMemcpyAsync(h_flags + off, a->d_flags + e0, (size_t)n, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = (int)e;
     }
     for (cudaStream_t s : ctx->streams) {

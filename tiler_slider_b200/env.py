@@ -10,10 +10,11 @@ through the C-ABI.  Only the Python exceptions of step() (RuntimeError after don
 TypeError on a non-enum action; environment.py:113-117) and the info dict are assembled on
 the host, from the flag byte the step kernel returns.
 
-Limits (ValueError): board size <= 16, at most 8 tiles, well-formed puzzles only (distinct
-tiles, none on a blocked cell) -- outside that domain the reference itself is erratic
-(SURVEY 7.0).  An empty tile list is accepted (nothing can move; state.py:183-186 decides
-the goal on the host since there is no move to compute).
+Limits (ValueError): board size <= 16, 1..8 tiles, well-formed puzzles only (distinct tiles,
+none on a blocked cell; outside that domain the reference itself is erratic), and
+in multi-colour mode as many targets as tiles (with a different count the reference can never
+report a win, state.py:183-184).  Nothing is ever computed on the host: there is no CPU
+fallback behind these classes.
 """
 from __future__ import annotations
 
@@ -49,12 +50,14 @@ class GameState:
         self._move_to = None
         self._locs = copy.copy(initial_locations)
         self._dirty = False
-        self._batch: Optional[BatchedTilerSliderEnv] = None
-        if len(initial_locations) > 0:
-            p = Puzzle(size, self._blocked, [(int(r), int(c)) for r, c in initial_locations],
-                       [(int(r), int(c)) for r, c in target_locations], bool(multi_color))
-            self._batch = BatchedTilerSliderEnv.from_puzzles([p], max_steps=_max_steps, auto_reset=False,
-                                                             device=device)
+        if len(initial_locations) == 0:
+            raise ValueError("a board needs at least one tile (the CUDA path has nothing to move otherwise)")
+        if multi_color and len(target_locations) != len(initial_locations):
+            raise ValueError("multi-colour boards need as many targets as tiles")
+        p = Puzzle(size, self._blocked, [(int(r), int(c)) for r, c in initial_locations],
+                   [(int(r), int(c)) for r, c in target_locations], bool(multi_color))
+        self._batch: BatchedTilerSliderEnv = BatchedTilerSliderEnv.from_puzzles(
+            [p], max_steps=_max_steps, auto_reset=False, device=device)
 
     # -- positions ------------------------------------------------------------------------
     @property
@@ -71,49 +74,28 @@ class GameState:
     def current_locations(self, locs):
         self._locs = list(locs)
         self._dirty = False
-        if self._batch is not None:
-            self._batch.set_positions(torch.tensor([[list(map(int, rc)) for rc in locs]], dtype=torch.uint8))
+        self._batch.set_positions(torch.tensor([[list(map(int, rc)) for rc in locs]], dtype=torch.uint8))
 
     # -- the move path ----------------------------------------------------------------------
     def move(self, move: Move) -> bool:
         """state.py:120-170 on the GPU; returns is_won()."""
-        if self._batch is None:
-            return self.is_won()
         flags = self._batch.raw_move(torch.tensor([move.value], dtype=torch.uint8))
         self._dirty = True
         return bool(int(flags[0]) & F_WON)
 
     def _env_step(self, move: Move) -> int:
         """One bookkept step (K2 with the env's max_steps); returns the flag byte."""
-        if self._batch is None:
-            return -1
         self._batch.step(torch.tensor([move.value], dtype=torch.uint8))
         self._dirty = True
         return int(self._batch.flags[0])
 
     def is_won(self) -> bool:
-        """state.py:172-186 on the current positions (ts_goal_check).  Without tiles there is
-        nothing on the device: the two (empty / target) lists are compared on the host."""
-        if self._batch is None:
-            tgt = [(int(r), int(c)) for r, c in self.target_locations]
-            return [] == tgt if self.multi_color else set() == set(tgt)
+        """state.py:172-186 on the current positions (ts_goal_check)."""
         return bool(self._batch.goal_check()[0])
 
     def get_state_array(self) -> np.ndarray:
         """state.py:188-211: float32[S,S,3] from K3."""
-        if self._batch is None or len(self.target_locations) != len(self._locs):
-            return self._host_obs()
         return self._batch.observe()[0].cpu().numpy()
-
-    def _host_obs(self) -> np.ndarray:
-        # only for boards the kernels do not hold (no tiles / ordered goal with a length mismatch)
-        s = np.zeros((self.size, self.size, 3), dtype=np.float32)
-        s[:, :, 0] = self.is_blocked.astype(np.float32)
-        for k, (i, j) in enumerate(self.current_locations):
-            s[i, j, 1] = k + 1 if self.multi_color else 1
-        for k, (i, j) in enumerate(self.target_locations):
-            s[i, j, 2] = k + 1 if self.multi_color else 1
-        return s
 
     @property
     def move_to(self) -> np.ndarray:
@@ -137,8 +119,6 @@ class GameState:
         return self._move_to
 
     def valid_moves(self) -> list[Move]:
-        if self._batch is None:
-            return []
         mask = int(self._batch.valid_moves()[0])
         return [m for m in Move if mask >> m.value & 1]
 
@@ -190,12 +170,8 @@ class TilerSliderEnv:
         if not isinstance(move, Move):
             raise TypeError(f"Action must be a GameState.Move enum, got {type(move)}")
         flags = self.state._env_step(move)
-        if flags < 0:   # no tiles: nothing moves, the goal is decided by the (empty) lists
-            won, invalid, timeout = self.state.is_won(), True, self.step_count + 1 >= self.max_steps
-            self.last_reward = 0.0
-        else:
-            won, invalid, timeout = bool(flags & F_WON), bool(flags & F_INVALID), bool(flags & F_TIMEOUT)
-            self.last_reward = float(self.state._batch.reward[0])
+        won, invalid, timeout = bool(flags & F_WON), bool(flags & F_INVALID), bool(flags & F_TIMEOUT)
+        self.last_reward = float(self.state._batch.reward[0])
         info = {"is_won": won, "step_count": self.step_count, "invalid_move": invalid}
         if won:
             self.done = True
