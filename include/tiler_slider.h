@@ -32,14 +32,10 @@
  *    per env.  S <= 6: BS = PS = S+1 and a WALL board also has column S of every row and all
  *    bits past the last row set (sentinels that end a slide; ts_encode / ts_synth write
  *    them).  S = 7, 8: BS = S, PS = 16, no sentinels.
- *  - wide boards (S >= 9): walls = u16 [action 0..3][capacity][16 lines], the
- *    board pre-oriented per action (line = row for LEFT/RIGHT, column for UP/DOWN; bit o = the
- *    cell at distance o from the end the move goes AWAY from; for S <= 15 bit S of every
- *    line is set as an edge sentinel), 128 bytes per env of which a step reads one 32-byte
- *    sector; set-goal target board = u16 [env][16 rows]; PS = 16.
- *  - step_count: uint8 per env when max_steps <= 255 (count_bytes = 1), else int32
- *    (count_bytes = 4).
- *  - actions: uint8 per env, 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (state.py:31-34).
+ *  - wide boards (S >= 9): walls = u16 [axis][capacity][16 lines]: plane 1 = rows (bit c of
+ *    line r), used by LEFT/RIGHT, plane 0 = columns (bit r of line c), used by UP/DOWN; for
+ *    S <= 15 bit S of every line is set as an edge sentinel; 64 bytes per env of which a step
+ *    reads one 32-byte sector.  Set-goal target board = u16 [capacity][16 rows].  PS = 16.
  */
 #ifndef TILER_SLIDER_H
 #define TILER_SLIDER_H

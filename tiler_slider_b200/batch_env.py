@@ -356,7 +356,7 @@ class BatchedTilerSliderEnv:
     def _board_cells(self, buf: torch.Tensor) -> torch.Tensor:
         """Unpack a plane-layout bitboard buffer to bool[N, S*S] (load-time / debugging aid)."""
         nb, cap, n = self.board_bytes, self.capacity, self.n_envs
-        if self.wide:   # u16 lines: walls [action][capacity][16] (action 3 = rows, bit c), targets [capacity][16]
+        if self.wide:   # u16 lines: walls [axis][capacity][16] (last plane = rows, bit c), targets [capacity][16]
             lines = buf.view(torch.int16).view(-1, cap, 16)[-1, :n].to(torch.int32) & 0xFFFF
             bits = (lines.unsqueeze(-1) >> torch.arange(16, device=buf.device)) & 1
             return bits[:, : self.size, : self.size].reshape(n, self.size * self.size).bool()

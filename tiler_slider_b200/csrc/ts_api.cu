@@ -76,18 +76,18 @@ __device__ __forceinline__ int wall_bit(const uint8_t* blocked_cells, int S, int
 // Write the wall board(s) of one env from a 0/1 cell map (all three board classes).
 __device__ void store_walls(uint8_t* d_walls, size_t cap, size_t env, int S, const uint8_t* cellmap) {
     if (wide_board(S)) {
-        uint16_t* w = reinterpret_cast<uint16_t*>(d_walls) + env * 16;   // [action][env][line]
+        uint16_t* w = reinterpret_cast<uint16_t*>(d_walls) + env * 16;   // [axis][env][line]
         const size_t plane = cap * 16;
         for (int l = 0; l < 16; ++l) {
-            uint32_t up = 0, down = 0, left = 0, right = 0;
-            if (l < S && S < 16) up = down = left = right = 1u << S;   // edge sentinel (ts_wide.cu)
+            uint32_t col = 0, row = 0;
+            if (l < S && S < 16) col = row = 1u << S;   // edge sentinel (ts_wide.cu)
             if (l < S)
                 for (int k = 0; k < S; ++k) {
-                    if (cellmap[k * S + l]) { down |= 1u << k; up |= 1u << (S - 1 - k); }      // column l
-                    if (cellmap[l * S + k]) { right |= 1u << k; left |= 1u << (S - 1 - k); }   // row l
+                    if (cellmap[k * S + l]) col |= 1u << k;    // column l, bit = row
+                    if (cellmap[l * S + k]) row |= 1u << k;    // row l, bit = column
                 }
-            w[0 * plane + l] = (uint16_t)up; w[1 * plane + l] = (uint16_t)down;
-            w[2 * plane + l] = (uint16_t)left; w[3 * plane + l] = (uint16_t)right;
+            w[0 * plane + l] = (uint16_t)col;
+            w[1 * plane + l] = (uint16_t)row;
         }
         return;
     }
@@ -126,7 +126,7 @@ __device__ void store_target_board(uint8_t* d_tb, size_t cap, size_t env, int S,
 }
 
 __device__ __forceinline__ bool wall_at(const uint8_t* d_walls, size_t cap, size_t env, int S, int r, int c) {
-    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_walls)[(3 * cap + env) * 16 + r] >> c) & 1;
+    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_walls)[(1 * cap + env) * 16 + r] >> c) & 1;
     return board_bit(d_walls, board_bytes(S), cap, env, r * board_stride(S) + c);
 }
 __device__ __forceinline__ bool target_at(const uint8_t* d_tb, size_t cap, size_t env, int S, int r, int c) {

@@ -17,8 +17,8 @@
 //                   indices stops there without any per-tile edge test.  Target boards (set
 //                   goal) use the same stride without sentinels.
 //   S = 7, 8 (compact boards): BS = S, PS = 16, no sentinels.
-//   S >= 9 (wide boards): PS = 16; walls are four pre-oriented 32-byte sectors per env
-//                   (walls[action][env][line] u16), the set-goal target board one sector
+//   S >= 9 (wide boards): PS = 16; walls are two 32-byte sectors per env, rows and columns
+//                   (walls[axis][env][line] u16), the set-goal target board one sector
 //                   (tboard[env][row] u16); see ts_wide.cu.
 //   capacity        allocation stride in envs, a multiple of 128 so that every plane start and
 //                   every 4-env group is 16-byte aligned
@@ -44,7 +44,7 @@ __host__ __device__ constexpr int board_bits(int S) { return S * board_stride(S)
 __host__ __device__ constexpr int board_bytes(int S) { return (board_bits(S) + 7) / 8; }
 // wide boards (S >= 9) do not fit 64 bits: env-major sectors of sixteen 16-bit lines, see ts_wide.cu
 __host__ __device__ constexpr bool wide_board(int S) { return S > 8; }
-__host__ __device__ constexpr int walls_bytes(int S) { return wide_board(S) ? 128 : board_bytes(S); }        // per env
+__host__ __device__ constexpr int walls_bytes(int S) { return wide_board(S) ? 64 : board_bytes(S); }        // per env
 __host__ __device__ constexpr int target_board_bytes(int S) { return wide_board(S) ? 32 : board_bytes(S); }  // per env, set goal
 
 // decomposition of nb bytes into planes of width 16 (repeated), 8, 4, 2, 1

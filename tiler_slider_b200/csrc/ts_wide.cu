@@ -6,17 +6,17 @@
 // 119-143), reset (environment.py:89-97), get_valid_moves (environment.py:149-171).
 //
 // A wide board does not fit a 64-bit word, so the bitboard tricks of ts_common.cuh do not
-// apply.  Layout (one 32-byte sector per env and orientation, orientation-major planes):
-//   walls[a][env][line]  u16, a = action (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT): the board
-//                        pre-oriented for that move -- `line` is the row (LEFT/RIGHT) or the
-//                        column (UP/DOWN) and bit o is the cell at distance o from the end of
-//                        the line the move goes AWAY from, i.e. a slide always goes toward
-//                        higher bits.  The walls are static, so the four
-//                        orientations are written once by ts_encode / ts_synth; a step reads
-//                        exactly ONE 32-byte sector of them (select-source load), never all.
-//                        (Planes, not [env][a]: ncu showed DRAM fetching the whole 128-byte
-//                        line around a sector, i.e. all four orientations of the env.)
-//                        For S <= 15 bit S of every line is stored as 1 (edge sentinel).
+// apply.  Layout (one 32-byte sector per env and axis, axis-major planes):
+//   walls[x][env][line]  u16, x = axis: plane 1 holds the rows (bit c of line r = cell (r,c)
+//                        blocked) and serves LEFT/RIGHT, plane 0 holds the columns (bit r of
+//                        line c) and serves UP/DOWN.  A step reads exactly ONE 32-byte sector
+//                        (select-source load); for UP/LEFT its lines are reversed in registers
+//                        so that every slide goes toward higher bits.  For S <= 15 bit S of every
+//                        line is stored as 1 (edge sentinel).
+//                        History (profiles/): with [env][4 orientations] DRAM fetched the whole
+//                        128-byte line around each sector (612 MB read per 4.2M-env launch instead
+//                        of 210 MB); four orientation planes cut that by a quarter, two axis
+//                        planes + in-register reversal by half.
 //   tboard[env][row]     u16 target cells (set goal only)
 //   position byte        row*16 + col
 // Thread = one env.  The 16 line words of the chosen orientation and the occupancy lines
@@ -48,6 +48,26 @@ template <int PW> __device__ __forceinline__ void st_pos(uint8_t* p, size_t env,
     else reinterpret_cast<uint2*>(p)[env] = make_uint2(q[0], q[1]);
 }
 
+// Fetch the env's 32-byte wall sector of the move's axis (plane 1 = rows for LEFT/RIGHT, plane 0 =
+// columns for UP/DOWN), turn it toward the move direction and park it in the thread's smem
+// column.  Stored lines run toward DOWN / RIGHT; for UP / LEFT (f = 1) every line is reversed
+// in registers: brev flips the pair word (both halves reversed and swapped), PRMT swaps the
+// halves back, a shift re-aligns the S cells and the edge sentinel (bit S, S <= 15) is put back.
+__device__ __forceinline__ void load_oriented_walls(WideSmem& sm, const uint4* sector, int S, uint32_t f) {
+    const uint4 b0 = __ldg(sector), b1 = __ldg(sector + 1);
+    uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    if (f) {
+        const uint32_t cells2 = ((1u << S) - 1u) * 0x00010001u;          // the S cell bits of both halves
+        const uint32_t sent2 = S < 16 ? (1u << S) * 0x00010001u : 0u;    // edge sentinels
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            w[k] = ((__byte_perm(__brev(w[k]), 0, 0x1032) >> (16 - S)) & cells2) | sent2;
+    }
+    uint32_t* wcol = &sm.w[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wcol[k * WIDE_THREADS] = w[k];
+}
+
 __device__ __forceinline__ uint32_t half_of(uint32_t word, uint32_t half) {
     return __byte_perm(word, 0, 0x4410u + half * 0x22u);   // half ? word >> 16 : word & 0xffff
 }
@@ -60,9 +80,7 @@ __device__ __forceinline__ void slide_wide16(WideSmem& sm, uint32_t (&q)[(T + 3)
     constexpr int PR = (T + 3) / 4;
     const int tid = threadIdx.x;
     const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
-    const uint4 b0 = __ldg(board), b1 = __ldg(board + 1);
-    sm.w[0][tid] = b0.x; sm.w[1][tid] = b0.y; sm.w[2][tid] = b0.z; sm.w[3][tid] = b0.w;
-    sm.w[4][tid] = b1.x; sm.w[5][tid] = b1.y; sm.w[6][tid] = b1.z; sm.w[7][tid] = b1.w;
+    load_oriented_walls(sm, board, S, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm.o[k][tid] = 0;
 
@@ -111,11 +129,9 @@ template <int T>
 __device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
     constexpr int PR = (T + 3) / 4;
     const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
-    const uint4 b0 = __ldg(board), b1 = __ldg(board + 1);
+    load_oriented_walls(sm, board, S, f);
     uint32_t* wcol = &sm.w[0][threadIdx.x];     // this thread's column: pair k at wcol[k * WIDE_THREADS]
     uint32_t* ocol = &sm.o[0][threadIdx.x];
-    wcol[0 * WIDE_THREADS] = b0.x; wcol[1 * WIDE_THREADS] = b0.y; wcol[2 * WIDE_THREADS] = b0.z; wcol[3 * WIDE_THREADS] = b0.w;
-    wcol[4 * WIDE_THREADS] = b1.x; wcol[5 * WIDE_THREADS] = b1.y; wcol[6 * WIDE_THREADS] = b1.z; wcol[7 * WIDE_THREADS] = b1.w;
 #pragma unroll
     for (int k = 0; k < 8; ++k) ocol[k * WIDE_THREADS] = 0;
 
@@ -183,8 +199,8 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_co
                                         : reinterpret_cast<const uint32_t*>(a.d_step_count)[env];
     const bool stale = !a.auto_reset && (a.d_flags[env] & F_DONE);
 
-    if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)action * (size_t)a.capacity + env) * 2, a.size, action);
-    else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)action * (size_t)a.capacity + env) * 2, a.size, action);
+    if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2, a.size, action);
+    else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2, a.size, action);
 
     bool moved = false, won = a.never_win == 0;
 #pragma unroll
@@ -239,8 +255,8 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_c
         uint32_t q[PR];
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
-        if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)d * (size_t)a.capacity + env) * 2, a.size, d);
-        else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)d * (size_t)a.capacity + env) * 2, a.size, d);
+        if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * 2, a.size, d);
+        else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * 2, a.size, d);
         bool moved = false;
 #pragma unroll
         for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
