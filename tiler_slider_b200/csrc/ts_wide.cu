@@ -29,6 +29,9 @@
 namespace ts {
 
 constexpr int WIDE_THREADS = 256;
+#ifndef WIDE_MIN_BLOCKS
+#define WIDE_MIN_BLOCKS 8
+#endif
 
 struct WideSmem {
     uint32_t w[8][WIDE_THREADS];   // wall lines, two 16-bit lines per word
@@ -184,7 +187,7 @@ __device__ __forceinline__ bool on_targets_wide(const uint32_t (&q)[(T + 3) / 4]
 }
 
 template <int T, int GOAL>
-__global__ void __launch_bounds__(WIDE_THREADS) wide_step_kernel(const __grid_constant__ ts_step_args a) {
+__global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kernel(const __grid_constant__ ts_step_args a) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
     __shared__ WideSmem sm;
     const int64_t i = (int64_t)blockIdx.x * WIDE_THREADS + threadIdx.x;
