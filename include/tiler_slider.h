@@ -215,6 +215,9 @@ int ts_goal_check(const ts_goal_args *a, void *stream);
  *                            seen before are appended to d_out_keys; d_counts[0] = append
  *                            cursor, d_counts[1] += #goal successors seen, d_counts[2] = 1 on
  *                            overflow of the table or of out_capacity
+ *   ts_bfs_traceback         follow the recorded parents from a goal state back to the root and
+ *                            emit the move string (the move between parent and child is found by
+ *                            re-running the four slides on the parent)
  * The exchange between partition and insert is an NCCL all-to-all done by the caller.
  * ------------------------------------------------------------------------------------- */
 #define TS_BFS_NONE 0xFFFFFFFFFFFFFFFFull
@@ -225,12 +228,25 @@ typedef struct ts_bfs_args {
     const uint8_t *d_walls, *d_targets_packed, *d_init;
     const uint64_t *d_in_keys;
     uint64_t *d_out_keys, *d_table, *d_counts;
+    /* optional parent tracking (single-rank searches): with d_table_parent given,
+     * ts_bfs_hash_insert records for every new key the key it was expanded from --
+     * d_in_keys[i] must then be exactly the output of ts_bfs_expand on d_parent_keys, so that
+     * the parent of d_in_keys[i] is d_parent_keys[i / 4]; d_parent_keys = NULL marks roots */
+    const uint64_t *d_parent_keys;
+    uint64_t *d_table_parent;
+    /* ts_bfs_traceback: d_in_keys[i] = goal state of item i (TS_BFS_NONE: none); writes the
+     * shortest move string of item i to d_moves[i * max_moves ...] (0..3, root first) and its
+     * length to d_lengths[i] (-1: no goal / longer than max_moves / broken chain) */
+    uint8_t *d_moves;
+    int32_t *d_lengths;
+    int64_t max_moves;
 } ts_bfs_args;
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
 int ts_bfs_expand(const ts_bfs_args *a, void *stream);
 int ts_bfs_partition_count(const ts_bfs_args *a, void *stream);
 int ts_bfs_partition_scatter(const ts_bfs_args *a, void *stream);
 int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
+int ts_bfs_traceback(const ts_bfs_args *a, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * ts_step_host: the same step through HOST buffers (the call a host-side driver makes):

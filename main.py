@@ -69,6 +69,8 @@ def main(argv=None) -> int:
     ap.add_argument("-max_steps", "--max-steps", dest="max_steps", type=int, default=None)
     ap.add_argument("-multi_color", "--multi-color", dest="multi_color", action="store_true",
                     help="force ordered tile/target matching for every puzzle of the file")
+    ap.add_argument("-solve", "--solve", action="store_true",
+                    help="also run the GPU breadth-first search and print a shortest solution per puzzle")
     ap.add_argument("-quiet", "--quiet", action="store_true")
     args = ap.parse_args(argv)
 
@@ -84,6 +86,13 @@ def main(argv=None) -> int:
                   f"{'multi' if p.multiple_colors else 'single'}-colour, moves '{moves}' ===")
         res = run_puzzle(p, moves, max_steps, args.quiet)
         print(f"result[{k}]: {res}")
+        if args.solve:
+            from tiler_slider_b200.bfs import BfsSolver
+            if p.size > 8:
+                print(f"solution[{k}]: BFS supports board sizes up to 8")
+            else:
+                r = BfsSolver([p], table_capacity=1 << 22).solve(with_paths=True)
+                print(f"solution[{k}]: {r.solutions[0]!r} (depth {r.solve_depth}, {r.n_states} reachable states)")
     return 0
 
 

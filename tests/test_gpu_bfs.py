@@ -65,6 +65,50 @@ def test_random_batches_vs_oracle_bfs(ts, S, T, W, multi, n):
     assert res.levels == [want_levels[d] for d in range(len(want_levels))]
 
 
+def _replay(b_or_args, moves):
+    size, blocked, tiles, targets, multi = b_or_args
+    st = orc.OracleState(size, blocked, tiles, targets, multi)
+    won_at = []
+    for k, ch in enumerate(moves):
+        if st.move("UDLR".index(ch)):
+            won_at.append(k + 1)
+    return won_at
+
+
+def test_shortest_solution_strings(ts, golden_misc):
+    """parent tracking + traceback.  Every solved puzzle gets a move string of
+    exactly its BFS solve depth that wins on its last move (replayed through the oracle) and
+    not earlier; unsolvable puzzles get None."""
+    from tiler_slider_b200.bfs import BfsSolver
+    from tests.helpers import random_puzzles
+    for b in golden_misc["bfs"]:
+        res = BfsSolver([puzzle_of(ts, b)], table_capacity=1 << 16).solve(with_paths=True)
+        sol = res.solutions[0]
+        if b["solve_depth"] < 0:
+            assert sol is None
+            continue
+        assert len(sol) == b["solve_depth"], (b["name"], sol)
+        assert _replay((b["size"], b["blocked"], b["tiles"], b["targets"], b["multi_color"]), sol) == [len(sol)]
+    S, T, W, n = 5, 2, 4, 64
+    rng = np.random.default_rng(12)
+    blocked, tiles, targets = random_puzzles(rng, n, S, T, W)
+    for multi in (True, False):
+        table = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi)
+        res = BfsSolver(table, table_capacity=1 << 18).solve(with_paths=True)
+        n_solved = 0
+        for e in range(n):
+            depth = int(res.solve_depth_per_puzzle[e])
+            sol = res.solutions[e]
+            if depth < 0:
+                assert sol is None
+                continue
+            n_solved += 1
+            bl = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+            assert len(sol) == depth
+            assert _replay((S, bl, tiles[e].tolist(), targets[e].tolist(), multi), sol)[:1] == [depth]
+        assert n_solved > 5
+
+
 def test_more_than_four_tiles_single_puzzle(ts):
     from tiler_slider_b200.bfs import solve_puzzle
     p = ts.Puzzle(5, [(2, 2), (0, 3)], [(0, 0), (0, 1), (1, 0), (4, 4), (3, 3)], [(4, 0), (4, 1), (4, 2), (4, 3), (0, 4)], False)

@@ -72,7 +72,9 @@ class BfsArgs(C.Structure):
                 ("reserved", _i32),
                 ("n_items", _i64), ("puzzle_capacity", _i64), ("table_capacity", _i64), ("out_capacity", _i64),
                 ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_in_keys", _vp),
-                ("d_out_keys", _vp), ("d_table", _vp), ("d_counts", _vp)]
+                ("d_out_keys", _vp), ("d_table", _vp), ("d_counts", _vp),
+                ("d_parent_keys", _vp), ("d_table_parent", _vp), ("d_moves", _vp), ("d_lengths", _vp),
+                ("max_moves", _i64)]
 
 
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
@@ -100,6 +102,7 @@ SYMBOLS = {
     "ts_bfs_partition_count": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_traceback": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "ts_host_ctx_destroy": (C.c_int, [_vp]),
     "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _vp, _i64]),

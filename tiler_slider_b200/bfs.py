@@ -46,6 +46,7 @@ class BfsResult:
     solve_depth_per_puzzle: torch.Tensor | None = None   # int32[P], -1 where unsolved within max_depth
     generated: int = 0                         # successors generated (state x move), all ranks
     per_level_seconds: list[float] = field(default_factory=list)
+    solutions: list[str | None] | None = None  # with_paths: a shortest move string per puzzle ('UDLR'), None if unsolved
 
 
 class CudaBfsKernels:
@@ -97,18 +98,36 @@ class CudaBfsKernels:
     def new_table(self, capacity: int) -> torch.Tensor:
         return torch.full((capacity,), NONE, dtype=torch.int64, device=self.device)
 
-    def insert(self, table: torch.Tensor, keys: torch.Tensor) -> tuple[torch.Tensor, int]:
-        """Insert keys; returns (keys that were new, with their goal bit; #goal successors seen)."""
+    def insert(self, table: torch.Tensor, keys: torch.Tensor, parents: torch.Tensor | None = None,
+               parent_table: torch.Tensor | None = None) -> tuple[torch.Tensor, int]:
+        """Insert keys; returns (keys that were new, with their goal bit; #goal successors seen).
+        With `parent_table` (same capacity as `table`) every new key also records its parent:
+        `parents` must be the frontier `keys` was expanded from (None for roots)."""
         out = torch.empty(keys.numel(), dtype=torch.int64, device=self.device)
         counts = torch.zeros(4, dtype=torch.int64, device=self.device)
         a = self._args(n_items=keys.numel(), table_capacity=table.numel(), out_capacity=out.numel(),
                        d_in_keys=keys.data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
-                       d_counts=counts.data_ptr())
+                       d_counts=counts.data_ptr(),
+                       d_parent_keys=None if parents is None else parents.data_ptr(),
+                       d_table_parent=None if parent_table is None else parent_table.data_ptr())
         self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
         n_new, n_won, overflow, _ = counts.tolist()
         if overflow:
             raise RuntimeError("BFS visited table is full: raise table_capacity")
         return out[:n_new], n_won
+
+
+    def traceback(self, table: torch.Tensor, parent_table: torch.Tensor, goals: torch.Tensor, max_moves: int):
+        """Shortest move strings of the goal states (NONE = no goal): (moves uint8[n, max_moves],
+        lengths int32[n])."""
+        n = goals.numel()
+        moves = torch.zeros(n, max_moves, dtype=torch.uint8, device=self.device)
+        lengths = torch.full((n,), -1, dtype=torch.int32, device=self.device)
+        a = self._args(n_items=n, table_capacity=table.numel(), d_in_keys=goals.data_ptr(), d_table=table.data_ptr(),
+                       d_table_parent=parent_table.data_ptr(), d_moves=moves.data_ptr(), d_lengths=lengths.data_ptr(),
+                       max_moves=max_moves)
+        self._call(self.lib.ts_bfs_traceback, a, "ts_bfs_traceback")
+        return moves, lengths
 
 
 class BfsSolver:
@@ -150,10 +169,16 @@ class BfsSolver:
         dist.all_reduce(t, group=self.group)
         return t.tolist()
 
-    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True) -> BfsResult:
+    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
+        """Search every puzzle to exhaustion (or max_depth).  with_paths (single rank only): also
+        record parents and return a shortest solution string per puzzle."""
         k, P = self.k, self.n_puzzles
+        if with_paths and (self.world > 1 or not per_puzzle):
+            raise ValueError("with_paths needs a single-rank search with per_puzzle statistics")
         table = k.new_table(self.table_capacity)
+        parent_table = k.new_table(self.table_capacity) if with_paths else None
         dev = k.device
+        goal_keys = torch.full((P,), NONE, dtype=torch.int64, device=dev) if with_paths else None
         states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
         depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
         single_puzzle_keys = getattr(k, "t", None) is not None and k.t.n_tiles > 4   # no id bits in the key
@@ -166,7 +191,7 @@ class BfsSolver:
         mine = self._exchange(seeds) if self.world > 1 else seeds
         if self.world > 1:   # every rank sent every seed: the owner received world copies; dedup does the rest
             pass
-        frontier, _ = k.insert(table, mine)
+        frontier, _ = k.insert(table, mine, None, parent_table) if with_paths else k.insert(table, mine)
         levels, generated, solve_depth = [], 0, -1
         n_new, = self._sum(frontier.numel())
         levels.append(n_new)
@@ -175,14 +200,18 @@ class BfsSolver:
         depth = 0
         while n_new > 0 and depth < max_depth:
             depth += 1
-            succ = k.expand(frontier & ~WON_BIT)
-            recv = self._exchange(succ)
+            parents = frontier & ~WON_BIT
+            succ = k.expand(parents)
+            recv = succ if with_paths else self._exchange(succ)     # paths: keep successor i next to parent i // 4
             if per_puzzle and recv.numel():
-                won = recv[recv < 0]                         # bit 63 set: goal met (NONE already dropped)
+                won = recv[(recv < 0) & (recv != NONE)]      # bit 63 set: goal met
                 if won.numel():
+                    if with_paths:                           # first goal state seen for a puzzle = a shortest solution
+                        fresh = won[depth_pp[pid_of(won)] >= (1 << 30)]
+                        goal_keys[pid_of(fresh)] = fresh
                     d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
                     depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
-            frontier, n_won = k.insert(table, recv)
+            frontier, n_won = k.insert(table, recv, parents, parent_table) if with_paths else k.insert(table, recv)
             n_new, n_won_all, gen = self._sum(frontier.numel(), n_won, 4 * (succ.numel() // 4))
             generated += gen
             if n_won_all and solve_depth < 0:
@@ -196,8 +225,14 @@ class BfsSolver:
             dist.all_reduce(depth_pp, op=dist.ReduceOp.MIN, group=self.group)
         if per_puzzle:
             depth_pp = torch.where(depth_pp >= (1 << 30), torch.full_like(depth_pp, -1), depth_pp)
+        solutions = None
+        if with_paths:
+            max_moves = max(1, int(depth_pp.max()))
+            moves, lengths = k.traceback(table, parent_table, goal_keys, max_moves)
+            mv, ln = moves.cpu().tolist(), lengths.cpu().tolist()
+            solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
         return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
-                         solve_depth_per_puzzle=depth_pp, generated=generated)
+                         solve_depth_per_puzzle=depth_pp, generated=generated, solutions=solutions)
 
 
 def solve_puzzle(puzzle: Puzzle, **kw) -> BfsResult:

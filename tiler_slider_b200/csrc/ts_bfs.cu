@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
     for (int64_t probe = 0; probe < a.table_capacity; ++probe) {
         const unsigned long long old = atomicCAS((unsigned long long*)&a.d_table[slot], (unsigned long long)BFS_NONE, (unsigned long long)key);
         if (old == BFS_NONE) {
+            if (a.d_table_parent) a.d_table_parent[slot] = a.d_parent_keys ? (a.d_parent_keys[i >> 2] & ~BFS_WON_BIT) : BFS_NONE;
             const unsigned long long pos = atomicAdd((unsigned long long*)&a.d_counts[0], 1ull);
             if ((int64_t)pos < a.out_capacity) a.d_out_keys[pos] = raw;
             else a.d_counts[2] = 1;
@@ -181,12 +182,67 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
     a.d_counts[2] = 1;
 }
 
+// slot of `key` in the visited table, or -1
+__device__ __forceinline__ int64_t table_find(const uint64_t* table, int64_t capacity, uint64_t key) {
+    const uint64_t mask = (uint64_t)capacity - 1;
+    uint64_t slot = mix64(key) & mask;
+    for (int64_t probe = 0; probe < capacity; ++probe) {
+        const uint64_t v = table[slot];
+        if (v == key) return (int64_t)slot;
+        if (v == BFS_NONE) return -1;
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
+// shortest move string of each goal state: walk the parent chain, recover every move by
+// re-sliding the parent (smallest move index that reproduces the child), reverse at the end
+template <int S, int T>
+__global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a) {
+    constexpr int PR = (T + 3) / 4, NB = board_bytes(S);
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= a.n_items) return;
+    uint8_t* out = a.d_moves + (size_t)i * a.max_moves;
+    uint64_t key = a.d_in_keys[i];
+    if (key == BFS_NONE) { a.d_lengths[i] = -1; return; }
+    key &= ~BFS_WON_BIT;
+    int len = 0;
+    bool ok = true;
+    while (ok) {
+        const int64_t slot = table_find(a.d_table, a.table_capacity, key);
+        if (slot < 0) { ok = false; break; }
+        const uint64_t parent = a.d_table_parent[slot];
+        if (parent == BFS_NONE) break;                     // reached a root
+        if (len >= a.max_moves) { ok = false; break; }
+        uint32_t q0[PR];
+        uint64_t pid;
+        split_key<T>(parent, q0, pid);
+        const uint64_t walls = load_board_elem<NB>(a.d_walls, (size_t)a.puzzle_capacity, (size_t)pid);
+        int move = -1;
+        for (uint32_t d = 0; d < 4 && move < 0; ++d) {
+            uint32_t q[PR];
+#pragma unroll
+            for (int w = 0; w < PR; ++w) q[w] = q0[w];
+            slide_env<S, T>(q, walls, d >> 1, (d & 1u) ^ 1u);
+            if (a.goal_mode == TS_GOAL_SET) sort_bytes<T>(q);
+            if (make_key<T>(q, pid) == key) move = (int)d;
+        }
+        if (move < 0) { ok = false; break; }
+        out[len++] = (uint8_t)move;
+        key = parent;
+    }
+    if (!ok) { a.d_lengths[i] = -1; return; }
+    for (int l = 0, r = len - 1; l < r; ++l, --r) { const uint8_t t = out[l]; out[l] = out[r]; out[r] = t; }
+    a.d_lengths[i] = len;
+}
+
 template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.n_items + 255) / 256);
 #define TS_BFS_CASE(T)                                                                  \
     case T:                                                                             \
         if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
-        else bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);                        \
+        else if (op == 1) bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);           \
+        else bfs_traceback_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
         break;
     switch (a.n_tiles) {
         TS_BFS_CASE(1) TS_BFS_CASE(2) TS_BFS_CASE(3) TS_BFS_CASE(4)
@@ -241,6 +297,14 @@ int ts_bfs_expand(const ts_bfs_args* a, void* stream) {
     if (a->n_items == 0) return 0;   // an empty local frontier is normal on a multi-rank search
     if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_out_keys) return TS_E_NULL_POINTER;
     return (int)bfs_dispatch(1, *a, (cudaStream_t)stream);
+}
+
+int ts_bfs_traceback(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (a->n_items == 0) return 0;
+    if (!a->d_walls || !a->d_in_keys || !a->d_table || !a->d_table_parent || !a->d_moves || !a->d_lengths) return TS_E_NULL_POINTER;
+    if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1)) || a->max_moves < 1) return TS_E_BAD_ARGUMENT;
+    return (int)bfs_dispatch(2, *a, (cudaStream_t)stream);
 }
 
 int ts_bfs_partition_count(const ts_bfs_args* a, void* stream) {
