@@ -4,7 +4,7 @@
 // Reference map (paths relative to the reference checkout):
 //   ts_encode   explainrl/environment/state.py:61-73        GameState.__init__ (is_blocked + lists)
 //   ts_synth    explainrl/environment/environment.py:221-226 create_simple_env recipe
-//   ts_observe  explainrl/environment/state.py:188-211      get_state_array
+//   ts_observe  explainrl/environment/state.py:188-211      get_state_array (kernel in ts_observe.cu)
 //   ts_step     see ts_step.cuh;  ts_valid_moves see ts_valid.cuh
 #include <cstdarg>
 #include <cstdio>
@@ -18,6 +18,7 @@ namespace ts {
     cudaError_t goal_dispatch_s##S(const ts_goal_args&, cudaStream_t);
 TS_DECL(1) TS_DECL(2) TS_DECL(3) TS_DECL(4) TS_DECL(5) TS_DECL(6) TS_DECL(7) TS_DECL(8)
 #undef TS_DECL
+cudaError_t observe_dispatch(const ts_observe_args&, cudaStream_t);
 cudaError_t wide_step_dispatch(const ts_step_args&, cudaStream_t);
 cudaError_t wide_valid_dispatch(const ts_valid_args&, cudaStream_t);
 cudaError_t wide_goal_dispatch(const ts_goal_args&, cudaStream_t);
@@ -208,31 +209,6 @@ __global__ void synth_kernel(const ts_synth_args a) {
     }
 }
 
-// ---- K3 observe ---------------------------------------------------------------------------------
-// thread = one cell of one env; a warp writes 32 cells x 3 channels = 384 contiguous bytes.
-__global__ void observe_kernel(const ts_observe_args a) {
-    const int S = a.size, T = a.n_tiles, cells = S * S, pw = pos_bytes(T);
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.n_envs * cells) return;
-    const int64_t i = idx / cells;
-    const int cell = (int)(idx - i * cells);
-    const size_t env = (size_t)(a.first_env + i), cap = (size_t)a.capacity;
-    const uint8_t rc = (uint8_t)((cell / S) * pos_stride(S) + (cell % S));
-    const float ch0 = wall_at(a.d_walls, cap, env, S, cell / S, cell % S) ? 1.0f : 0.0f;
-    float ch1 = 0.0f, ch2 = 0.0f;
-    const bool ordered = a.goal_mode == TS_GOAL_ORDERED;
-    for (int t = 0; t < T; ++t)
-        if (a.d_pos[env * pw + t] == rc) ch1 = ordered ? (float)(t + 1) : 1.0f;
-    if (ordered) {
-        for (int t = 0; t < T; ++t)
-            if (a.d_targets_packed[env * pw + t] == rc) ch2 = (float)(t + 1);
-    } else {
-        ch2 = target_at(a.d_targets_packed, cap, env, S, cell / S, cell % S) ? 1.0f : 0.0f;
-    }
-    float* o = a.d_obs + (size_t)idx * 3;
-    o[0] = ch0; o[1] = ch1; o[2] = ch2;
-}
-
 }  // namespace ts
 
 using namespace ts;
@@ -319,10 +295,8 @@ int ts_observe(const ts_observe_args* a, void* stream) {
     if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
     if (!a->d_walls || !a->d_targets_packed || !a->d_pos || !a->d_obs) return fail(TS_E_NULL_POINTER, "null device pointer");
     if (a->n_envs == 0) return 0;
-    const int64_t n = a->n_envs * a->size * a->size;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    observe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
-    return cuda_result(cudaGetLastError(), "ts_observe launch");
+    if (!aligned16(a->d_obs)) return fail(TS_E_MISALIGNED, "d_obs %p is not 16-byte aligned", (const void*)a->d_obs);
+    return cuda_result(observe_dispatch(*a, (cudaStream_t)stream), "ts_observe launch");
 }
 
 int ts_valid_moves(const ts_valid_args* a, void* stream) {

@@ -193,6 +193,23 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) 
     return d;
 }
 
+// element `idx` of a plane-layout board buffer as a 64-bit board
+template <int NB> __device__ __forceinline__ uint64_t load_board_elem(const uint8_t* base, size_t cap, size_t idx) {
+    uint64_t b = 0;
+    static_for<0, plane_count(NB)>([&](auto I) {
+        constexpr int k = decltype(I)::value;
+        constexpr int w = plane_width(NB, k), off = plane_offset(NB, k);
+        const uint8_t* p = base + (size_t)off * cap + idx * w;
+        uint64_t v;
+        if constexpr (w == 8) v = *reinterpret_cast<const uint64_t*>(p);
+        else if constexpr (w == 4) v = *reinterpret_cast<const uint32_t*>(p);
+        else if constexpr (w == 2) v = *reinterpret_cast<const uint16_t*>(p);
+        else v = *p;
+        b |= v << (8 * off);
+    });
+    return b;
+}
+
 // ---- SWAR helpers on 4 packed position bytes -------------------------------------------------
 __device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {
     return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);

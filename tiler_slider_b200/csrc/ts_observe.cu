@@ -1,0 +1,100 @@
+// ts_observe.cu -- K3: dense observation, GameState.get_state_array
+// (explainrl/environment/state.py:188-211): float32 [N][S][S][3] (HWC) -- ch0 blocked (0/1), ch1
+// tile index+1 (ordered goal) or 1 (set goal), ch2 target index+1 or 1; later indices overwrite
+// earlier ones (state.py:202-209).
+//
+// A pure HBM writer: 12*S*S bytes per env against ~14 bytes read, and almost every float is
+// zero.  So the kernel does not compute floats, it scatters the few non-zeros: a block owns E
+// consecutive envs (about 28 KB of output), zero-fills their image in shared memory with
+// 16-byte stores, drops in the walls (one bit test per cell), the tiles and the targets (one
+// thread per env, in index order, so that a later index overwrites an earlier one exactly as
+// the reference's loops do), and streams the image out with 16-byte coalesced stores.
+// History (profiles/experiments/observe_throughput.py, 6x6 / 4 tiles, GB/s written): thread per
+// cell with runtime S and per-byte loops 1227; thread per cell, compile-time S, SWAR matching
+// 2442; this kernel: see README.
+#include "ts_common.cuh"
+#include "../../include/tiler_slider.h"
+
+namespace ts {
+
+constexpr int OBS_THREADS = 256;
+__host__ __device__ constexpr int obs_envs_per_block(int S) {
+    int e = 7168 / (S * S * 3);
+    e = e > 64 ? 64 : e;
+    e &= ~3;                       // multiple of 4: a block's output starts 16-byte aligned for odd S too
+    return e < 4 ? 4 : e;
+}
+
+template <int S>
+__global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_args a) {
+    constexpr int CELLS = S * S, PER_ENV = CELLS * 3, NB = board_bytes(S), E = obs_envs_per_block(S);
+    __shared__ __align__(16) float stage[E * PER_ENV];
+    const int64_t env0 = (int64_t)blockIdx.x * E;
+    const int n_here = (int)min((int64_t)E, a.n_envs - env0);
+    const size_t cap = (size_t)a.capacity;
+    const bool ordered = a.goal_mode == TS_GOAL_ORDERED;
+    const int T = a.n_tiles, pw = pos_bytes(T);
+    const int n_floats = n_here * PER_ENV;
+
+    for (int k = threadIdx.x; k < (E * PER_ENV) / 4; k += OBS_THREADS)
+        reinterpret_cast<float4*>(stage)[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncthreads();
+
+    // walls (and set-goal targets): one bit test per cell
+    for (int j = threadIdx.x; j < n_here * CELLS; j += OBS_THREADS) {
+        const int e = j / CELLS, cell = j - e * CELLS;
+        const int r = cell / S, c = cell - r * S;
+        const size_t env = (size_t)(a.first_env + env0 + e);
+        bool wall, tgt = false;
+        if constexpr (wide_board(S)) {
+            wall = (reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * 16 + r] >> c) & 1;   // plane 1 = rows
+            if (!ordered) tgt = (reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * 16 + r] >> c) & 1;
+        } else {
+            const int bit = r * board_stride(S) + c;
+            wall = (load_board_elem<NB>(a.d_walls, cap, env) >> bit) & 1ull;
+            if (!ordered) tgt = (load_board_elem<NB>(a.d_targets_packed, cap, env) >> bit) & 1ull;
+        }
+        if (wall) stage[j * 3] = 1.0f;
+        if (tgt) stage[j * 3 + 2] = 1.0f;
+    }
+    // tiles and ordered targets: one thread per env, ascending index (later overwrites earlier)
+    for (int e = threadIdx.x; e < n_here; e += OBS_THREADS) {
+        const size_t env = (size_t)(a.first_env + env0 + e);
+        const uint8_t* pp = a.d_pos + env * pw;
+        const uint8_t* tp = a.d_targets_packed + env * pw;
+        float* img = stage + e * PER_ENV;
+        for (int k = 0; k < T; ++k) {
+            const int b = pp[k];
+            img[((b / pos_stride(S)) * S + b % pos_stride(S)) * 3 + 1] = ordered ? (float)(k + 1) : 1.0f;
+            if (ordered) {
+                const int t = tp[k];
+                img[((t / pos_stride(S)) * S + t % pos_stride(S)) * 3 + 2] = (float)(k + 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    float* out = a.d_obs + env0 * PER_ENV;          // 16-byte aligned: E * PER_ENV is a multiple of 4
+    for (int k = threadIdx.x; k * 4 < n_floats; k += OBS_THREADS) {
+        if (k * 4 + 3 < n_floats) __stcs(reinterpret_cast<float4*>(out) + k, reinterpret_cast<const float4*>(stage)[k]);
+        else for (int j = k * 4; j < n_floats; ++j) out[j] = stage[j];
+    }
+}
+
+template <int S> static void launch_observe(const ts_observe_args& a, cudaStream_t st) {
+    constexpr int E = obs_envs_per_block(S);
+    observe_kernel<S><<<(unsigned)((a.n_envs + E - 1) / E), OBS_THREADS, 0, st>>>(a);
+}
+
+cudaError_t observe_dispatch(const ts_observe_args& a, cudaStream_t st) {
+    switch (a.size) {
+#define TS_OBS(S) case S: launch_observe<S>(a, st); break;
+        TS_OBS(1) TS_OBS(2) TS_OBS(3) TS_OBS(4) TS_OBS(5) TS_OBS(6) TS_OBS(7) TS_OBS(8)
+        TS_OBS(9) TS_OBS(10) TS_OBS(11) TS_OBS(12) TS_OBS(13) TS_OBS(14) TS_OBS(15) TS_OBS(16)
+#undef TS_OBS
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace ts
