@@ -240,6 +240,10 @@ typedef struct ts_bfs_args {
     uint8_t *d_moves;
     int32_t *d_lengths;
     int64_t max_moves;
+    /* ts_bfs_hash_insert, optional: the first won_capacity goal successors seen (duplicates
+     * included) are also copied to d_won_keys, in the order of d_counts[1] */
+    uint64_t *d_won_keys;
+    int64_t won_capacity;
 } ts_bfs_args;
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
 int ts_bfs_expand(const ts_bfs_args *a, void *stream);

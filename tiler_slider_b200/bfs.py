@@ -52,12 +52,16 @@ class BfsResult:
 class CudaBfsKernels:
     """ctypes front-end of the ts_bfs_* entry points for one puzzle table."""
 
+    WON_CAPACITY = 1 << 16
+
     def __init__(self, table: BatchedTilerSliderEnv):
         if table.size > 8:
             raise ValueError("BFS supports board sizes up to 8")
         if table.n_tiles > 4 and table.n_envs > 1:
             raise ValueError("more than 4 tiles: the key has no room for a puzzle id, solve one puzzle at a time")
         self.t, self.lib, self.device = table, lib(), table.device
+        self._won_buf = None
+        self.last_won = None
 
     def _args(self, **kw) -> BfsArgs:
         t = self.t
@@ -105,15 +109,20 @@ class CudaBfsKernels:
         `parents` must be the frontier `keys` was expanded from (None for roots)."""
         out = torch.empty(keys.numel(), dtype=torch.int64, device=self.device)
         counts = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if self._won_buf is None:
+            self._won_buf = torch.empty(self.WON_CAPACITY, dtype=torch.int64, device=self.device)
         a = self._args(n_items=keys.numel(), table_capacity=table.numel(), out_capacity=out.numel(),
                        d_in_keys=keys.data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
                        d_counts=counts.data_ptr(),
                        d_parent_keys=None if parents is None else parents.data_ptr(),
-                       d_table_parent=None if parent_table is None else parent_table.data_ptr())
+                       d_table_parent=None if parent_table is None else parent_table.data_ptr(),
+                       d_won_keys=self._won_buf.data_ptr(), won_capacity=self.WON_CAPACITY)
         self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
-        n_new, n_won, overflow, _ = counts.tolist()
+        n_new, n_won, overflow, _ = counts.tolist()              # the one host sync of a BFS level
         if overflow:
             raise RuntimeError("BFS visited table is full: raise table_capacity")
+        # goal successors of this call (duplicates included); None if there were too many to buffer
+        self.last_won = self._won_buf[:n_won].clone() if n_won <= self.WON_CAPACITY else None
         return out[:n_new], n_won
 
 
@@ -186,32 +195,33 @@ class BfsSolver:
         def pid_of(keys):
             return torch.zeros_like(keys) if single_puzzle_keys else (keys >> 32) & 0x7FFFFFFF
 
-        # depth 0: every rank seeds all puzzles and keeps the keys it owns
+        # depth 0: every rank seeds all puzzles and keeps the keys it owns (the owner receives one
+        # copy per rank; dedup keeps one)
         seeds = k.seed()
         mine = self._exchange(seeds) if self.world > 1 else seeds
-        if self.world > 1:   # every rank sent every seed: the owner received world copies; dedup does the rest
-            pass
         frontier, _ = k.insert(table, mine, None, parent_table) if with_paths else k.insert(table, mine)
         levels, generated, solve_depth = [], 0, -1
         n_new, = self._sum(frontier.numel())
         levels.append(n_new)
-        if per_puzzle and frontier.numel():
-            states_pp.index_add_(0, pid_of(frontier), torch.ones_like(frontier))
+        frontiers = [frontier] if per_puzzle else None        # per-puzzle state counts are taken once, at the end
         depth = 0
         while n_new > 0 and depth < max_depth:
             depth += 1
             parents = frontier & ~WON_BIT
             succ = k.expand(parents)
-            recv = succ if with_paths else self._exchange(succ)     # paths: keep successor i next to parent i // 4
-            if per_puzzle and recv.numel():
-                won = recv[(recv < 0) & (recv != NONE)]      # bit 63 set: goal met
-                if won.numel():
-                    if with_paths:                           # first goal state seen for a puzzle = a shortest solution
-                        fresh = won[depth_pp[pid_of(won)] >= (1 << 30)]
-                        goal_keys[pid_of(fresh)] = fresh
-                    d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
-                    depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
+            # single rank: successors go straight to the table (it skips NONE) and successor i stays
+            # next to its parent i // 4; several ranks: bucket by owner and exchange
+            recv = succ if self.world == 1 else self._exchange(succ)
             frontier, n_won = k.insert(table, recv, parents, parent_table) if with_paths else k.insert(table, recv)
+            if per_puzzle and n_won:
+                won = getattr(k, "last_won", None)
+                if won is None:                              # stand-in kernels / overflowed buffer: scan
+                    won = recv[(recv < 0) & (recv != NONE)]
+                if with_paths:                               # first goal state seen for a puzzle = a shortest solution
+                    fresh = won[depth_pp[pid_of(won)] >= (1 << 30)]
+                    goal_keys[pid_of(fresh)] = fresh
+                d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
+                depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
             n_new, n_won_all, gen = self._sum(frontier.numel(), n_won, 4 * (succ.numel() // 4))
             generated += gen
             if n_won_all and solve_depth < 0:
@@ -219,7 +229,11 @@ class BfsSolver:
             if n_new:
                 levels.append(n_new)
                 if per_puzzle:
-                    states_pp.index_add_(0, pid_of(frontier), torch.ones_like(frontier))
+                    frontiers.append(frontier)
+        if per_puzzle:
+            pids = torch.cat([pid_of(f) for f in frontiers]) if frontiers else torch.zeros(0, dtype=torch.int64, device=dev)
+            if pids.numel():
+                states_pp += torch.bincount(pids, minlength=P)[:P]
         if per_puzzle and self.world > 1:
             dist.all_reduce(states_pp, group=self.group)
             dist.all_reduce(depth_pp, op=dist.ReduceOp.MIN, group=self.group)

@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
     const uint64_t raw = a.d_in_keys[i];
     if (raw == BFS_NONE) return;
     const uint64_t key = raw & ~BFS_WON_BIT;
-    if (raw & BFS_WON_BIT) atomicAdd((unsigned long long*)&a.d_counts[1], 1ull);
+    if (raw & BFS_WON_BIT) {
+        const unsigned long long w = atomicAdd((unsigned long long*)&a.d_counts[1], 1ull);
+        if (a.d_won_keys && (int64_t)w < a.won_capacity) a.d_won_keys[w] = raw;
+    }
     const uint64_t mask = (uint64_t)a.table_capacity - 1;
     uint64_t slot = mix64(key) & mask;
     for (int64_t probe = 0; probe < a.table_capacity; ++probe) {
