@@ -159,24 +159,24 @@ class BfsSolver:
         self.table_capacity = table_capacity
 
     # ---- one exchange: every key travels to the rank that owns it -------------------------
-    def _exchange(self, keys: torch.Tensor) -> torch.Tensor:
+    def _exchange(self, keys: torch.Tensor) -> tuple[torch.Tensor, bool]:
+        """Returns (keys this rank owns, anything_sent_anywhere).  Two collectives: an
+        all_gather of the per-owner bucket sizes of every rank -- it doubles as the termination
+        test, a search is over when no rank has anything to send -- and the all-to-all of the
+        keys themselves."""
         if self.world == 1:
-            return keys[keys != NONE]
+            return keys, bool(keys.numel())
         send, sizes = self.k.partition(keys, self.world)
-        send_sizes = torch.tensor(sizes, dtype=torch.int64, device=send.device)
-        recv_sizes = torch.empty_like(send_sizes)
-        dist.all_to_all_single(recv_sizes, send_sizes, group=self.group)
-        rs = recv_sizes.tolist()
+        mine = torch.tensor(sizes, dtype=torch.int64, device=send.device)
+        allsz = torch.empty(self.world * self.world, dtype=torch.int64, device=send.device)
+        dist.all_gather_into_tensor(allsz, mine, group=self.group)
+        m = allsz.view(self.world, self.world).tolist()              # m[src][dst]
+        rs = [m[src][self.rank] for src in range(self.world)]
+        if not any(any(row) for row in m):
+            return send[:0], False
         recv = torch.empty(sum(rs), dtype=torch.int64, device=send.device)
         dist.all_to_all_single(recv, send, rs, sizes, group=self.group)
-        return recv
-
-    def _sum(self, *vals: int) -> list[int]:
-        if self.world == 1:
-            return list(vals)
-        t = torch.tensor(vals, dtype=torch.int64, device=self.k.device)
-        dist.all_reduce(t, group=self.group)
-        return t.tolist()
+        return recv, True
 
     def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
         """Search every puzzle to exhaustion (or max_depth).  with_paths (single rank only): also
@@ -197,21 +197,22 @@ class BfsSolver:
 
         # depth 0: every rank seeds all puzzles and keeps the keys it owns (the owner receives one
         # copy per rank; dedup keeps one)
-        seeds = k.seed()
-        mine = self._exchange(seeds) if self.world > 1 else seeds
+        mine, _ = self._exchange(k.seed())
         frontier, _ = k.insert(table, mine, None, parent_table) if with_paths else k.insert(table, mine)
-        levels, generated, solve_depth = [], 0, -1
-        n_new, = self._sum(frontier.numel())
-        levels.append(n_new)
+        # per-rank tallies; summed over the ranks once, after the search
+        local_levels, local_won, generated = [frontier.numel()], [0], 0
         frontiers = [frontier] if per_puzzle else None        # per-puzzle state counts are taken once, at the end
         depth = 0
-        while n_new > 0 and depth < max_depth:
-            depth += 1
+        while depth < max_depth:
             parents = frontier & ~WON_BIT
             succ = k.expand(parents)
             # single rank: successors go straight to the table (it skips NONE) and successor i stays
             # next to its parent i // 4; several ranks: bucket by owner and exchange
-            recv = succ if self.world == 1 else self._exchange(succ)
+            recv, alive = self._exchange(succ)
+            if not alive:
+                break
+            depth += 1
+            generated += succ.numel()
             frontier, n_won = k.insert(table, recv, parents, parent_table) if with_paths else k.insert(table, recv)
             if per_puzzle and n_won:
                 won = getattr(k, "last_won", None)
@@ -222,14 +223,21 @@ class BfsSolver:
                     goal_keys[pid_of(fresh)] = fresh
                 d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
                 depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
-            n_new, n_won_all, gen = self._sum(frontier.numel(), n_won, 4 * (succ.numel() // 4))
-            generated += gen
-            if n_won_all and solve_depth < 0:
-                solve_depth = depth
-            if n_new:
-                levels.append(n_new)
-                if per_puzzle:
-                    frontiers.append(frontier)
+            local_levels.append(frontier.numel())
+            local_won.append(n_won)
+            if per_puzzle and frontier.numel():
+                frontiers.append(frontier)
+        # ---- tallies over all ranks (every rank ran the same number of levels) ---------------
+        tally = torch.tensor([local_levels, local_won], dtype=torch.int64, device=dev)
+        gen = torch.tensor([generated], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(tally, group=self.group)
+            dist.all_reduce(gen, group=self.group)
+        levels, won_per_level = tally[0].tolist(), tally[1].tolist()
+        while len(levels) > 1 and levels[-1] == 0:
+            levels.pop()
+        solve_depth = next((d for d, w in enumerate(won_per_level) if w), -1)
+        generated = int(gen.item())
         if per_puzzle:
             pids = torch.cat([pid_of(f) for f in frontiers]) if frontiers else torch.zeros(0, dtype=torch.int64, device=dev)
             if pids.numel():

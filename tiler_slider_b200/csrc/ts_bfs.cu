@@ -115,27 +115,53 @@ __device__ __forceinline__ uint32_t key_owner(uint64_t key, uint32_t n_ranks) {
     return (uint32_t)((mix64(key & ~BFS_WON_BIT) >> 40) % n_ranks);
 }
 
+// Warp-aggregated bucket bookkeeping: lanes holding keys of the same owner elect a leader
+// (__match_any_sync) that bumps the block's shared counter once for all of them; with 2-8 owners
+// and a billion keys a per-key atomic on 2-8 addresses is what the exchange would wait for.
+// Returns this lane's slot inside the block's share of its owner's bucket.
+__device__ __forceinline__ uint32_t block_bucket_slot(unsigned int* hist, bool live, uint32_t owner) {
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+    uint32_t slot = 0;
+    if (live) {
+        const unsigned peers = __match_any_sync(active, owner);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&hist[owner], (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        slot = base + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    }
+    return slot;
+}
+
 __global__ void __launch_bounds__(256) bfs_partition_count_kernel(const ts_bfs_args a) {
     __shared__ unsigned int hist[64];
     if (threadIdx.x < 64) hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < a.n_items) {
-        const uint64_t key = a.d_in_keys[i];
-        if (key != BFS_NONE) atomicAdd(&hist[key_owner(key, (uint32_t)a.n_ranks)], 1u);
-    }
+    const uint64_t key = i < a.n_items ? a.d_in_keys[i] : BFS_NONE;
+    const bool live = key != BFS_NONE;
+    block_bucket_slot(hist, live, live ? key_owner(key, (uint32_t)a.n_ranks) : 0u);
     __syncthreads();
     if (threadIdx.x < a.n_ranks && hist[threadIdx.x]) atomicAdd((unsigned long long*)&a.d_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
-// d_counts holds, on entry, the write cursor (= exclusive prefix offset) of every owner bucket
+// d_counts holds, on entry, the write cursor (= exclusive prefix offset) of every owner bucket;
+// a block reserves its share of each bucket with one global atomic per owner
 __global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs_args a) {
+    __shared__ unsigned int hist[64];
+    __shared__ unsigned long long base[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.n_items) return;
-    const uint64_t key = a.d_in_keys[i];
-    if (key == BFS_NONE) return;
-    const unsigned long long slot = atomicAdd((unsigned long long*)&a.d_counts[key_owner(key, (uint32_t)a.n_ranks)], 1ull);
-    a.d_out_keys[slot] = key;
+    const uint64_t key = i < a.n_items ? a.d_in_keys[i] : BFS_NONE;
+    const bool live = key != BFS_NONE;
+    const uint32_t owner = live ? key_owner(key, (uint32_t)a.n_ranks) : 0u;
+    const uint32_t slot = block_bucket_slot(hist, live, owner);
+    __syncthreads();
+    if (threadIdx.x < a.n_ranks && hist[threadIdx.x])
+        base[threadIdx.x] = atomicAdd((unsigned long long*)&a.d_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+    __syncthreads();
+    if (live) a.d_out_keys[base[owner] + slot] = key;
 }
 
 // K5: insert keys into the open-addressing visited table (EMPTY = all ones).  New keys are
