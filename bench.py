@@ -42,8 +42,8 @@ ALGO_BYTES = 3 * T + (S * S + 7) // 8 + 8      # 25 B per env-step
 METRIC = "env-steps/sec at 1/2/4/8 B200 and % HBM roofline vs reference CPU step loop"
 UNIT = "env-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default
-# size, from the committed `ncu --set full` capture (profiles/r1_v3_step_kernel_full_raw.csv)
-NCU_TRAFFIC_BYTES = {"c3": 268.447488e6 + 135.936256e6}
+# size, from the committed `ncu --set full` capture (profiles/r1_final_step_kernel_full_raw.csv)
+NCU_TRAFFIC_BYTES = {"c3": 268.460032e6 + 138.960640e6}
 N_ACTION_ROWS = 8                               # distinct pre-generated action vectors, cycled
 
 
