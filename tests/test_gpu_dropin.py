@@ -116,6 +116,20 @@ def test_gamestate_surface(ts, golden_misc):
     assert ts.Move.from_char("u") is ts.Move.UP and ts.Move.from_int(3) is ts.Move.RIGHT and ts.Move.from_char("q") is None
 
 
+def test_constructor_accepts_what_the_reference_accepts(ts):
+    """tests/test_state.py:614-642 of the reference only construct a 20x20 board and a 20-tile
+    board and read attributes; construction is lazy here, so that works, and the limits of the
+    kernels (S <= 16, T <= 8) surface as ValueError on first use."""
+    big = ts.GameState(20, [(10, 10)], [(0, 0)], [(19, 19)], False)
+    assert big.size == 20 and big.is_blocked.shape == (20, 20) and big.is_blocked[10, 10]
+    many = ts.GameState(10, [], [(i // 10, i % 10) for i in range(20)], [(9 - i // 10, 9 - i % 10) for i in range(20)], False)
+    assert len(many.current_locations) == 20
+    with pytest.raises(ValueError):
+        big.move(ts.Move.UP)
+    with pytest.raises(ValueError):
+        many.get_state_array()
+
+
 def test_factory(ts, golden_misc):
     for f in golden_misc["factory"]:
         env = ts.TilerSliderEnvFactory.create_simple_env(**f["kwargs"])

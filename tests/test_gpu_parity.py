@@ -154,8 +154,10 @@ def test_ordered_goal_length_mismatch_is_rejected(ts):
     targets = np.array([[[0, 2], [2, 2]]], np.uint8)
     with pytest.raises(ValueError, match="as many targets as tiles"):
         ts.BatchedTilerSliderEnv.from_arrays(3, blocked, tiles, targets, True)
-    with pytest.raises(ValueError):
-        ts.GameState(3, [], [], [(0, 0)], False)
+    empty = ts.GameState(3, [], [], [(0, 0)], False)          # recording the board is fine (lazy device state) ...
+    assert empty.size == 3 and len(empty.current_locations) == 0
+    with pytest.raises(ValueError, match="at least one tile"):
+        empty.is_won()                                          # ... computing on it is not
 
 
 def test_observation_valid_moves_goal(ts):

@@ -50,14 +50,27 @@ class GameState:
         self._move_to = None
         self._locs = copy.copy(initial_locations)
         self._dirty = False
-        if len(initial_locations) == 0:
-            raise ValueError("a board needs at least one tile (the CUDA path has nothing to move otherwise)")
-        if multi_color and len(target_locations) != len(initial_locations):
-            raise ValueError("multi-colour boards need as many targets as tiles")
-        p = Puzzle(size, self._blocked, [(int(r), int(c)) for r, c in initial_locations],
-                   [(int(r), int(c)) for r, c in target_locations], bool(multi_color))
-        self._batch: BatchedTilerSliderEnv = BatchedTilerSliderEnv.from_puzzles(
-            [p], max_steps=_max_steps, auto_reset=False, device=device)
+        self._initial = copy.copy(initial_locations)
+        self._batch_obj: Optional[BatchedTilerSliderEnv] = None
+
+    @property
+    def _batch(self) -> BatchedTilerSliderEnv:
+        """The batch-of-one CUDA environment, built on first use: constructing a GameState only
+        records the board (like the reference's constructor, it accepts any size and tile count);
+        shapes the kernels do not cover raise ValueError when the first move / goal check /
+        observation is asked for."""
+        if self._batch_obj is None:
+            if len(self._initial) == 0:
+                raise ValueError("a board needs at least one tile (the CUDA path has nothing to move otherwise)")
+            if self.multi_color and len(self.target_locations) != len(self._initial):
+                raise ValueError("multi-colour boards need as many targets as tiles")
+            p = Puzzle(self.size, self._blocked, [(int(r), int(c)) for r, c in self._initial],
+                       [(int(r), int(c)) for r, c in self.target_locations], bool(self.multi_color))
+            self._batch_obj = BatchedTilerSliderEnv.from_puzzles([p], max_steps=self._max_steps, auto_reset=False,
+                                                                 device=self._device)
+            if self._locs != self._initial:      # positions assigned before the first use
+                self._batch_obj.set_positions(torch.tensor([[list(map(int, rc)) for rc in self._locs]], dtype=torch.uint8))
+        return self._batch_obj
 
     # -- positions ------------------------------------------------------------------------
     @property
@@ -74,7 +87,8 @@ class GameState:
     def current_locations(self, locs):
         self._locs = list(locs)
         self._dirty = False
-        self._batch.set_positions(torch.tensor([[list(map(int, rc)) for rc in locs]], dtype=torch.uint8))
+        if self._batch_obj is not None:
+            self._batch_obj.set_positions(torch.tensor([[list(map(int, rc)) for rc in locs]], dtype=torch.uint8))
 
     # -- the move path ----------------------------------------------------------------------
     def move(self, move: Move) -> bool:
