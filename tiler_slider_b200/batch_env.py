@@ -17,8 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (CAP_ALIGN, F_DONE, F_INVALID, F_STALE, F_TIMEOUT, F_WON, GOAL_ORDERED, GOAL_SET, MAX_SIZE,
-                   MAX_TILES, EncodeArgs, GoalArgs, ObserveArgs, StepArgs, SynthArgs, ValidArgs, check, lib)
+from ._lib import (CAP_ALIGN, F_WON, GOAL_ORDERED, GOAL_SET, MAX_SIZE, MAX_TILES, EncodeArgs, GoalArgs, ObserveArgs,
+                   StepArgs, SynthArgs, ValidArgs, check, lib)
 from .puzzle import Puzzle, as_puzzle, uniform_shape
 
 DEFAULT_REWARDS = (1.0, -0.01, -0.05)   # r_win, r_step, r_invalid -- repo-defined (the reference has no reward)
@@ -90,6 +90,7 @@ class BatchedTilerSliderEnv:
         self._terminal = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev) if track_terminal else None
         self._scratch_count = None
         self._scratch_flags = None
+        self._scratch_reward = None
         self._host_ctx = None
         self._cached_args = None
         self._cached_out = None
@@ -261,10 +262,11 @@ class BatchedTilerSliderEnv:
         self._scratch_flags.zero_()
         a = self._step_args(self._stage_actions(actions), count=self._scratch_count, flags=self._scratch_flags,
                             max_steps=2 ** 31 - 1, count_bytes=4, auto_reset=False, raw=True)
-        saved_reward = self._reward.clone()
+        if self._scratch_reward is None:
+            self._scratch_reward = torch.zeros(self.capacity, dtype=torch.float32, device=self.device)
+        a.d_reward = self._scratch_reward.data_ptr()          # the episode's reward buffer stays untouched
         with torch.cuda.device(self.device):
             check(self._lib.ts_step(C.byref(a), self._stream()), "ts_step")
-        self._reward.copy_(saved_reward)
         return self._scratch_flags[: self.n_envs]
 
     # ------------------------------------------------------------------ host-buffer path

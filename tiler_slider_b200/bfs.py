@@ -29,7 +29,7 @@ from typing import Sequence
 import torch
 import torch.distributed as dist
 
-from ._lib import GOAL_SET, BfsArgs, check, lib
+from ._lib import BfsArgs, check, lib
 from .batch_env import BatchedTilerSliderEnv
 from .puzzle import Puzzle
 

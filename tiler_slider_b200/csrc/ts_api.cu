@@ -1,5 +1,5 @@
 // ts_api.cu -- C-ABI entry points (include/tiler_slider.h), argument validation, and the
-// load-time kernels: K1 ts_encode, K0 ts_synth, K3 ts_observe.
+// load-time kernels: K1 ts_encode, K0 ts_synth (K3 ts_observe lives in ts_observe.cu).
 //
 // Reference map (paths relative to the reference checkout):
 //   ts_encode   explainrl/environment/state.py:61-73        GameState.__init__ (is_blocked + lists)
@@ -59,9 +59,6 @@ __device__ __forceinline__ size_t board_byte_addr(int nb, size_t cap, size_t env
         off += w;
     }
     return 0;
-}
-__device__ __forceinline__ bool board_bit(const uint8_t* base, int nb, size_t cap, size_t env, int bit) {
-    return (base[board_byte_addr(nb, cap, env, bit >> 3)] >> (bit & 7)) & 1;
 }
 
 // value of bit `bit` of a stored WALL board: blocked cells, plus (padded boards) the sentinel
@@ -124,15 +121,6 @@ __device__ void store_target_board(uint8_t* d_tb, size_t cap, size_t env, int S,
         }
         d_tb[board_byte_addr(nb, cap, env, b)] = (uint8_t)v;
     }
-}
-
-__device__ __forceinline__ bool wall_at(const uint8_t* d_walls, size_t cap, size_t env, int S, int r, int c) {
-    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_walls)[(1 * cap + env) * 16 + r] >> c) & 1;
-    return board_bit(d_walls, board_bytes(S), cap, env, r * board_stride(S) + c);
-}
-__device__ __forceinline__ bool target_at(const uint8_t* d_tb, size_t cap, size_t env, int S, int r, int c) {
-    if (wide_board(S)) return (reinterpret_cast<const uint16_t*>(d_tb)[env * 16 + r] >> c) & 1;
-    return board_bit(d_tb, board_bytes(S), cap, env, r * board_stride(S) + c);
 }
 
 // ---- K1 encode --------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ from typing import Any, Dict, Optional, Tuple
 import numpy as np
 import torch
 
-from ._lib import F_DONE, F_INVALID, F_TIMEOUT, F_WON
+from ._lib import F_INVALID, F_TIMEOUT, F_WON
 from .batch_env import BatchedTilerSliderEnv
 from .moves import Move
 from .puzzle import Puzzle, parse_board_text
