@@ -133,6 +133,36 @@ def c_oracle_rate(n_envs: int = 4096, steps: int = 200):
     return n_envs * steps / (time.perf_counter() - t0)
 
 
+def parity_check(ts, dev, n_envs: int = 8192, steps: int = 128) -> dict:
+    """The parity run that accompanies the throughput number: the first n_envs
+    puzzles of the bench workload, `steps` random actions, every position / flag / reward of the
+    CUDA path compared with the C oracle (the checker, part of the cpu_baseline leg)."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    env = ts.BatchedTilerSliderEnv.synthetic(n_envs, S, T, W_WALLS, MULTI, seed=PUZZLE_SEED, max_steps=MAX_STEPS,
+                                             auto_reset=True, track_terminal=True, device=dev)
+    blocked = env.blocked_cells().cpu().numpy().astype(np.uint8)
+    tiles = env.positions().cpu().numpy()
+    if env.goal_mode == ts.GOAL_ORDERED:
+        targets = env.target_positions().cpu().numpy()
+    else:
+        cells = np.stack([np.flatnonzero(r) for r in env.target_positions().cpu().numpy()])
+        targets = np.stack([cells // S, cells % S], -1).astype(np.uint8)
+    gen = torch.Generator(device=dev).manual_seed(ACTION_SEED)
+    actions = torch.randint(0, 4, (steps, env.capacity), dtype=torch.uint8, device=dev, generator=gen)
+    want = orc.rollout(S, MULTI, blocked, tiles, targets, actions[:, :n_envs].cpu().numpy(), max_steps=MAX_STEPS, auto_reset=True)
+    bad = 0
+    for k in range(steps):
+        _, r, d = env.step(actions[k])
+        post = torch.where(d[:, None, None], env.positions(env.terminal_pos), env.positions())
+        bad += int((post.cpu().numpy() != want["pos"][k]).any(axis=(1, 2)).sum())
+        bad += int((env.flags.cpu().numpy() != want["flags"][k]).sum())
+        bad += int((r.cpu().numpy() != want["reward"][k]).sum())
+    return {"env_steps_checked": n_envs * steps, "mismatches": bad, "fields": "positions, flags (done/won/invalid/timeout), reward",
+            "checker": "oracle/ts_oracle.c"}
+
+
 def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -324,6 +354,7 @@ def run_ours(args) -> int:
                                     "sample": f"{n_cpu} envs x 300 steps of the same workload, single process, "
                                               "oracle/py_port.py (reference Python step loop restated)",
                                     "c_oracle_env_steps_per_s_1core": c_oracle_rate()}
+            line["parity"] = parity_check(ts, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
