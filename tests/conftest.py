@@ -23,6 +23,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts: compile the CUDA library (nvcc cross-compiles
+    # without a GPU) and the C oracle once, before collection
+    from tiler_slider_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH) and not os.environ.get("TS_LIB_PATH"):
+        _lib.build()
+    from oracle import oracle as _orc
+    _orc.build()
 
 
 @pytest.fixture(scope="session")
