@@ -21,7 +21,10 @@
  *  - There is no CPU fallback anywhere in this library.
  *
  * Packed layout (struct-of-arrays, environment index innermost):
- *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.
+ *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.  EVERY per-env
+ *    array handed to the library (state, actions, reward, done, flags, ...) must hold
+ *    `capacity` elements: kernels work on whole 4-env groups / 128-env tiles and may read and
+ *    write the padding environments between n_envs and capacity (their content is unspecified).
  *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = row*PS + col of tile
  *    i (PS = ts_pos_stride(S)), unused bytes zero.  Arrays: pos (in/out), init, targets
  *    (ordered mode).
