@@ -204,3 +204,39 @@ def test_stale_freeze_without_auto_reset():
     assert got["flags"][:, 0].tolist() == [orc.F_DONE | orc.F_WON, orc.F_DONE | orc.F_STALE, orc.F_DONE | orc.F_STALE]
     assert got["pos"][:, 0, 0].tolist() == [[0, 2]] * 3
     assert got["reward"][:, 0].tolist() == [1.0, 0.0, 0.0]
+
+
+def test_c_oracle_and_python_port_agree_on_random_boards():
+    """The two restatements were written independently (C with an explicit used list, Python
+    with the reference's own containers); on 150 random boards of every size 1..12, both colour
+    modes, 0-8 tiles' worth of traffic they must agree step by step, including the flags."""
+    from tests.helpers import random_puzzles
+    rng = np.random.default_rng(99)
+    checked = 0
+    for trial in range(150):
+        S = int(rng.integers(1, 13))
+        T = int(rng.integers(1, min(8, S * S) + 1))
+        W = int(rng.integers(0, max(1, (S * S - 2 * T) // 2 + 1))) if S * S - 2 * T > 0 else 0
+        if W + 2 * T > S * S:
+            continue
+        multi = bool(rng.integers(0, 2))
+        max_steps = int(rng.integers(1, 12))
+        blocked, tiles, targets = random_puzzles(rng, 1, S, T, W)
+        K = 24
+        actions = rng.integers(0, 4, size=(K, 1), dtype=np.uint8)
+        got = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=True)
+        b = [(c // S, c % S) for c in np.flatnonzero(blocked[0])]
+        env = py_port.PortEnv(S, b, [tuple(map(int, t)) for t in tiles[0]], [tuple(map(int, t)) for t in targets[0]],
+                              multi, max_steps)
+        env.reset()
+        for k in range(K):
+            _, done, info = env.step(int(actions[k, 0]))
+            assert [[int(r), int(c)] for r, c in env.state.current_locations] == got["pos"][k, 0].tolist()
+            f = int(got["flags"][k, 0])
+            assert (done, info["is_won"], info["invalid_move"], bool(info.get("timeout"))) == \
+                (bool(f & 1), bool(f & 2), bool(f & 4), bool(f & 8))
+            assert info["step_count"] == got["count"][k, 0]
+            if done:
+                env.reset()
+            checked += 1
+    assert checked > 2500
