@@ -123,3 +123,30 @@ def test_table_overflow_is_reported(ts, golden_misc):
     b = [x for x in golden_misc["bfs"] if x["name"] == "puzzle_multi_180"][0]
     with pytest.raises(RuntimeError, match="table is full"):
         solve_puzzle(puzzle_of(ts, b), table_capacity=256)
+
+
+def test_level_corpus_on_gpu(ts):
+    """All 400 real levels of the reference (tests/golden/levels_400.txt) through the product
+    path: text loader -> batches per shape -> BFS with parent tracking.  State counts and solve
+    depths must equal the oracle's BFS, and every returned move string must solve its puzzle on
+    its last move when replayed through the oracle."""
+    import os
+    from tiler_slider_b200.bfs import BfsSolver
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels_400.txt")
+    puzzles = ts.load_puzzle_file(path)
+    assert len(puzzles) == 400
+    groups = {}
+    for p in puzzles:
+        groups.setdefault((p.size, len(p.initial_locations), p.multiple_colors), []).append(p)
+    n_checked = 0
+    for (S, T, multi), ps in groups.items():
+        res = BfsSolver(ps, table_capacity=1 << 20).solve(with_paths=True)
+        for i, p in enumerate(ps):
+            st = orc.OracleState(S, p.blocked_locations, p.initial_locations, p.target_locations, multi)
+            n, _, depth, _ = st.bfs()
+            assert int(res.states_per_puzzle[i]) == n and int(res.solve_depth_per_puzzle[i]) == depth
+            sol = res.solutions[i]
+            assert sol is not None and len(sol) == depth
+            assert _replay((S, p.blocked_locations, p.initial_locations, p.target_locations, multi), sol) == [depth]
+            n_checked += 1
+    assert n_checked == 400

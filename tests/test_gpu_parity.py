@@ -343,6 +343,37 @@ def live_after_reset(env):
     return (env.flags & (F_DONE | F_STALE)) == 0
 
 
+def test_real_levels_step_parity(ts):
+    """The reference's 400 real levels (tests/golden/levels_400.txt, decoded by its own image
+    parser): 96 random steps each with auto-reset and max_steps 25, every field against the oracle."""
+    import os
+    puzzles = ts.load_puzzle_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels_400.txt"))
+    groups = {}
+    for p in puzzles:
+        groups.setdefault((p.size, len(p.initial_locations), p.multiple_colors), []).append(p)
+    rng = np.random.default_rng(400)
+    total = 0
+    for (S, T, multi), ps in groups.items():
+        n, K = len(ps), 96
+        blocked = np.zeros((n, S * S), np.uint8)
+        for i, p in enumerate(ps):
+            for r, c in p.blocked_locations:
+                blocked[i, r * S + c] = 1
+        tiles = np.array([p.initial_locations for p in ps], np.uint8).reshape(n, T, 2)
+        targets = np.array([p.target_locations for p in ps], np.uint8).reshape(n, T, 2)
+        actions = rng.integers(0, 4, size=(K, n), dtype=np.uint8)
+        want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=25, auto_reset=True)
+        env = ts.BatchedTilerSliderEnv.from_puzzles(ps, max_steps=25, auto_reset=True, track_terminal=True)
+        for k in range(K):
+            _, r, d = env.step(torch.as_tensor(actions[k]).cuda())
+            post = torch.where(d[:, None, None], env.positions(env.terminal_pos), env.positions())
+            assert np.array_equal(post.cpu().numpy(), want["pos"][k])
+            assert np.array_equal(env.flags.cpu().numpy(), want["flags"][k])
+            assert np.array_equal(r.cpu().numpy(), want["reward"][k])
+        total += n * K
+    assert total == 400 * 96
+
+
 def test_cuda_graph_replay_matches_eager(ts):
     S, T, W, N, R = 5, 1, 5, 10_000, 8
     a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, False, seed=4, auto_reset=True)

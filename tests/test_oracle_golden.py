@@ -240,3 +240,41 @@ def test_c_oracle_and_python_port_agree_on_random_boards():
                 env.reset()
             checked += 1
     assert checked > 2500
+
+
+def _levels():
+    import os
+    from tests.helpers import parse_text
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels_400.txt")
+    out, grid, multi = [], [], False
+    for ln in open(here).read().splitlines() + ["---"]:
+        s = ln.strip()
+        if s.startswith("#") or not s:
+            continue
+        if s.startswith("multi_color:"):
+            multi = s.split(":")[1].strip() == "true"
+        elif set(s) <= {"-"}:
+            size, blocked, tiles, targets = parse_text("\n".join(grid))
+            out.append((size, blocked, tiles, targets, multi))
+            grid, multi = [], False
+        else:
+            grid.append(s)
+    return out
+
+
+def test_level_corpus_bfs():
+    """Real puzzles: the reference's 400 levels (decoded by its own image parser,
+    tests/golden/make_levels.py).  For every 8th level a plain BFS over the reference's move
+    recorded state count, level histogram and solve depth (tests/golden/make_levels_bfs.py); the
+    C oracle's BFS must reproduce them.  Every level of the shipped corpus is solvable."""
+    import json
+    import os
+    levels = _levels()
+    assert len(levels) == 400
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels_bfs.json")))
+    for g in gold:
+        size, blocked, tiles, targets, multi = levels[g["index"]]
+        n, lv, depth, _ = orc.OracleState(size, blocked, tiles, targets, multi).bfs()
+        assert (n, lv, depth) == (g["n_states"], g["levels"], g["solve_depth"]), g["index"]
+    solved = sum(orc.OracleState(*lv).bfs()[2] > 0 for lv in levels)
+    assert solved == 400
