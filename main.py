@@ -63,8 +63,11 @@ def run_puzzle(puzzle, moves: str, max_steps: int, quiet: bool = False) -> dict:
 
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description="Tiler-Slider on B200: load puzzles from a text file and play scripted moves")
-    ap.add_argument("-input_file", "--input-file", "--input_file", dest="input_file", required=True,
+    ap.add_argument("-input_file", "--input-file", "--input_file", dest="input_file", default=None,
                     help="puzzle text file (grammar of create_from_string)")
+    ap.add_argument("-level", "--level", default=None,
+                    help="level screenshot by name, e.g. puzzle_multi_001 (the reference's play.py --level)")
+    ap.add_argument("-data_dir", "--data-dir", dest="data_dir", default="data", help="directory of the level screenshots")
     ap.add_argument("-moves", "--moves", default=None, help="action string over UDLR; overrides the file's `moves:` lines")
     ap.add_argument("-max_steps", "--max-steps", dest="max_steps", type=int, default=None)
     ap.add_argument("-multi_color", "--multi-color", dest="multi_color", action="store_true",
@@ -75,7 +78,13 @@ def main(argv=None) -> int:
     args = ap.parse_args(argv)
 
     from tiler_slider_b200 import load_puzzle_file
-    puzzles = load_puzzle_file(args.input_file)
+    if (args.input_file is None) == (args.level is None):
+        ap.error("give exactly one of -input_file and -level")
+    if args.level is not None:
+        from tiler_slider_b200.levels import load_level
+        puzzles = [load_level(args.level, args.data_dir)]
+    else:
+        puzzles = load_puzzle_file(args.input_file)
     for k, p in enumerate(puzzles):
         if args.multi_color:
             p.multiple_colors = True

@@ -5,6 +5,8 @@ Public surface (reference names kept):
   Move                                               action enum (state.py:29-45)
   BatchedTilerSliderEnv                              N boards per GPU, one kernel launch per step
   Puzzle, parse_board_text, load_puzzle_file         text grammar + `-input_file` loader
+  levels.load_level / load_level_image               screenshot ingest (host-side, cv2)
+  bfs.BfsSolver                                      batched breadth-first search, NCCL dedup
 Every computation runs in libtiler_slider.so (hand-written sm_100a CUDA, C-ABI in
 include/tiler_slider.h); there is no CPU fallback.
 """
