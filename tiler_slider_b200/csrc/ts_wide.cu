@@ -186,24 +186,30 @@ __device__ __forceinline__ bool on_targets_wide(const uint32_t (&q)[(T + 3) / 4]
     return all;
 }
 
-template <int T, int GOAL>
+// AR: auto-reset on / off (off: finished envs are frozen and report STALE); S16: board size 16
+// (lines without a stored sentinel).  32-bit env index: ts_step rejects larger batches.
+template <int T, int GOAL, bool AR, bool S16>
 __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kernel(const __grid_constant__ ts_step_args a) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
     __shared__ WideSmem sm;
-    const int64_t i = (int64_t)blockIdx.x * WIDE_THREADS + threadIdx.x;
-    if (i >= a.n_envs) return;
-    const size_t env = (size_t)(a.first_env + i);
+    const uint32_t i = blockIdx.x * WIDE_THREADS + threadIdx.x;
+    if (i >= (uint32_t)a.n_envs) return;
+    const uint32_t env = (uint32_t)a.first_env + i;
     const uint32_t action = a.d_actions[env] & 3u;
     uint32_t q0[PR], q[PR];
     ld_pos<PW>(a.d_pos, env, q0);
 #pragma unroll
     for (int w = 0; w < PR; ++w) q[w] = q0[w];
-    uint32_t count = a.count_bytes == 1 ? (uint32_t)reinterpret_cast<const uint8_t*>(a.d_step_count)[env]
-                                        : reinterpret_cast<const uint32_t*>(a.d_step_count)[env];
-    const bool stale = !a.auto_reset && (a.d_flags[env] & F_DONE);
+    const bool narrow = a.count_bytes == 1;
+    uint32_t count = narrow ? (uint32_t)reinterpret_cast<const uint8_t*>(a.d_step_count)[env]
+                            : reinterpret_cast<const uint32_t*>(a.d_step_count)[env];
+    bool stale = false;
+    if constexpr (!AR) stale = (a.d_flags[env] & F_DONE) != 0;
+    const float r_win = a.r_win, r_step = a.r_step, r_invalid = a.r_invalid;
 
-    if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2, a.size, action);
-    else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2, a.size, action);
+    const uint4* sector = reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2;
+    if constexpr (S16) slide_wide16<T>(sm, q, sector, 16, action);
+    else slide_wide<T>(sm, q, sector, a.size, action);
 
     bool moved = false, won = a.never_win == 0;
 #pragma unroll
@@ -220,24 +226,26 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kerne
     const bool timeout = (int)count >= a.max_steps;
     bool done = won || timeout;
     uint32_t flags = (done ? F_DONE : 0u) | (won ? F_WON : 0u) | (moved ? 0u : F_INVALID) | (timeout ? F_TIMEOUT : 0u);
-    float reward = won ? a.r_win : (moved ? a.r_step : a.r_invalid);
-    if (stale) {   // frozen: the reference raises here (environment.py:113-114)
-        flags = F_DONE | F_STALE;
-        reward = 0.0f;
-        count -= 1u;
-        done = true;
+    float reward = won ? r_win : (moved ? r_step : r_invalid);
+    if constexpr (!AR) {
+        if (stale) {   // frozen: the reference raises here (environment.py:113-114)
+            flags = F_DONE | F_STALE;
+            reward = 0.0f;
+            count -= 1u;
+            done = true;
 #pragma unroll
-        for (int w = 0; w < PR; ++w) q[w] = q0[w];
+            for (int w = 0; w < PR; ++w) q[w] = q0[w];
+        }
     }
     if (done) {
         if (a.d_terminal_pos) st_pos<PW>(a.d_terminal_pos, env, q);
-        if (a.auto_reset) {   // environment.py:89-97
+        if constexpr (AR) {   // environment.py:89-97
             ld_pos<PW>(a.d_init, env, q);
             count = 0;
         }
     }
     st_pos<PW>(a.d_pos, env, q);
-    if (a.count_bytes == 1) reinterpret_cast<uint8_t*>(a.d_step_count)[env] = (uint8_t)count;
+    if (narrow) reinterpret_cast<uint8_t*>(a.d_step_count)[env] = (uint8_t)count;
     else reinterpret_cast<uint32_t*>(a.d_step_count)[env] = count;
     a.d_reward[env] = reward;
     if (a.d_done) a.d_done[env] = done ? 1 : 0;
@@ -288,10 +296,18 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_goal_kernel(const __grid_co
     a.d_won[env] = won ? 1 : 0;
 }
 
+template <int T, int GOAL> static void launch_wide_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t st) {
+    const bool ar = a.auto_reset != 0, s16 = a.size == 16;
+    if (ar && !s16) wide_step_kernel<T, GOAL, true, false><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    else if (ar) wide_step_kernel<T, GOAL, true, true><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    else if (!s16) wide_step_kernel<T, GOAL, false, false><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    else wide_step_kernel<T, GOAL, false, true><<<blocks, WIDE_THREADS, 0, st>>>(a);
+}
 template <int T> static cudaError_t launch_wide_step(const ts_step_args& a, cudaStream_t st) {
+    if (a.first_env + a.n_envs >= ((int64_t)1 << 32)) return cudaErrorInvalidValue;   // 32-bit env index
     const unsigned blocks = (unsigned)((a.n_envs + WIDE_THREADS - 1) / WIDE_THREADS);
-    if (a.goal_mode == TS_GOAL_ORDERED) wide_step_kernel<T, TS_GOAL_ORDERED><<<blocks, WIDE_THREADS, 0, st>>>(a);
-    else wide_step_kernel<T, TS_GOAL_SET><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    if (a.goal_mode == TS_GOAL_ORDERED) launch_wide_step_goal<T, TS_GOAL_ORDERED>(a, blocks, st);
+    else launch_wide_step_goal<T, TS_GOAL_SET>(a, blocks, st);
     return cudaGetLastError();
 }
 
