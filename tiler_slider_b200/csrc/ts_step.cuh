@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
 #ifndef TS_PIPE_STAGES
 #define TS_PIPE_STAGES 2
 #endif
+#ifndef TS_PIPE_MINBLOCKS
+#define TS_PIPE_MINBLOCKS 1
+#endif
 constexpr int PIPE_THREADS = TS_PIPE_THREADS;
 constexpr int PIPE_STAGES = TS_PIPE_STAGES;
 
@@ -322,7 +325,7 @@ template <int W> __device__ __forceinline__ void words_from_smem(uint32_t (&r)[W
 }
 
 template <int S, int T, int GOAL, bool AR>
-__global__ void __launch_bounds__(PIPE_THREADS) step_kernel_pipe(const __grid_constant__ ts_step_args a) {
+__global__ void __launch_bounds__(PIPE_THREADS, TS_PIPE_MINBLOCKS) step_kernel_pipe(const __grid_constant__ ts_step_args a) {
     using L = PipeLayout<S, T, GOAL, AR>;
     constexpr int PW = L::PW, NB = L::NB;
     extern __shared__ __align__(128) uint8_t smem[];
