@@ -273,7 +273,7 @@ template <int S> __device__ __forceinline__ DirParams dir_params(uint32_t h, uin
 }
 
 template <int S, int T>
-__device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, const DirParams& dp) {
+__device__ __forceinline__ bool slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_t walls, const DirParams& dp) {
     using PD = Padded<S>;
     constexpr int PR = (T + 3) / 4;
     const uint32_t st = dp.st, lm = dp.lm, fm = dp.fm, fk = dp.fk;
@@ -309,13 +309,16 @@ __device__ __forceinline__ void slide_padded(uint32_t (&q)[(T + 3) / 4], uint64_
         }
         ACC[i / 4] = mad_u32((uint32_t)__popc(empty), 1u << (8 * (i % 4)), ACC[i / 4]);
     });
+    uint32_t any = 0;
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
         const uint32_t pn = st * ACC[w] + P[w];
         q[w] = pn * fm + fk;
+        any |= ACC[w];
     }
     // unused bytes of the last word stay zero: KREV4-(KREV4-0) = 0 and nothing is accumulated
     // into them (the flipped value KREV of an unused byte is never read as a tile).
+    return any != 0;                                       // a tile moved iff some count is non-zero
 }
 
 template <int S, int T>

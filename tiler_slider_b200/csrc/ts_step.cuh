@@ -89,16 +89,15 @@ __device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, St
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
         in.walls.get(e, bw);
+        bool moved = false;
         if constexpr (padded_board(S)) {
             const uint4 d = dir_tab[(in.act4 >> (8 * e)) & 3u];
-            slide_padded<S, T>(q, board64(bw), DirParams{d.x, d.y, d.z, d.w});
+            moved = slide_padded<S, T>(q, board64(bw), DirParams{d.x, d.y, d.z, d.w});   // no q0 kept alive
         } else {
             slide_env<S, T>(q, board64(bw), (h4 >> (8 * e)) & 0xFFu, (f4 >> (8 * e)) & 0xFFu);
-        }
-
-        bool moved = false;
 #pragma unroll
-        for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
+            for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
+        }
         bool won = can_win;
         if constexpr (GOAL == TS_GOAL_ORDERED) {
             uint32_t tq[PR];
@@ -206,6 +205,10 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     const size_t e0 = (size_t)g * GROUP;
 
     StepInputs<S, T, GOAL, CW> in;
+    // targets and step counters are only needed after the slide; under the 32-register cap the
+    // compiler sinks their loads to that point, so pull the lines into L2 now (no register cost)
+    if constexpr (GOAL == TS_GOAL_ORDERED) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d_targets_packed + e0 * PW));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(a.d_step_count) + (size_t)g * (GROUP * CW)));
     ld_words<PW>(a.d_pos + e0 * PW, in.praw);
     in.walls.load(a.d_walls, cap, g);
     if constexpr (GOAL == TS_GOAL_ORDERED) ld_words<PW>(a.d_targets_packed + e0 * PW, in.traw);
