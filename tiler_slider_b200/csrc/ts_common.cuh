@@ -73,33 +73,41 @@ template <int B, int E, class F> __device__ __forceinline__ void static_for(F&& 
     if constexpr (B < E) { f(IC<B>{}); static_for<B + 1, E>(f); }
 }
 
+// cache policy of the streaming accesses (overridable for experiments: -D'TS_LD(p)=__ldg(p)')
+#ifndef TS_LD
+#define TS_LD(p) __ldcs(p)
+#endif
+#ifndef TS_ST
+#define TS_ST(p, v) __stcs(p, v)
+#endif
+
 // ---- streaming global access ---------------------------------------------------------------
 // Every stream is touched once per step and the working set (>=400 MB at 16M envs) exceeds
 // the 126 MB L2, so loads/stores carry the evict-first (.cs) policy.
 template <int WORDS> __device__ __forceinline__ void ld_words(const void* p, uint32_t (&r)[WORDS]) {
     if constexpr (WORDS == 1) {
-        r[0] = __ldcs(reinterpret_cast<const unsigned int*>(p));
+        r[0] = TS_LD(reinterpret_cast<const unsigned int*>(p));
     } else if constexpr (WORDS == 2) {
-        uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+        uint2 v = TS_LD(reinterpret_cast<const uint2*>(p));
         r[0] = v.x; r[1] = v.y;
     } else {
         static_assert(WORDS % 4 == 0, "group loads are 4, 8 or 16*k bytes");
 #pragma unroll
         for (int k = 0; k < WORDS / 4; ++k) {
-            uint4 v = __ldcs(reinterpret_cast<const uint4*>(p) + k);
+            uint4 v = TS_LD(reinterpret_cast<const uint4*>(p) + k);
             r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
         }
     }
 }
 template <int WORDS> __device__ __forceinline__ void st_words(void* p, const uint32_t (&r)[WORDS]) {
     if constexpr (WORDS == 1) {
-        __stcs(reinterpret_cast<unsigned int*>(p), r[0]);
+        TS_ST(reinterpret_cast<unsigned int*>(p), r[0]);
     } else if constexpr (WORDS == 2) {
-        __stcs(reinterpret_cast<uint2*>(p), make_uint2(r[0], r[1]));
+        TS_ST(reinterpret_cast<uint2*>(p), make_uint2(r[0], r[1]));
     } else {
 #pragma unroll
         for (int k = 0; k < WORDS / 4; ++k)
-            __stcs(reinterpret_cast<uint4*>(p) + k, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+            TS_ST(reinterpret_cast<uint4*>(p) + k, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
     }
 }
 

@@ -171,11 +171,11 @@ __device__ __forceinline__ void step_group(const ts_step_args& a, uint32_t g, St
 
     // ---- stores --------------------------------------------------------------------------------
     st_words<PW>(a.d_pos + e0 * PW, pnew);
-    if constexpr (CW == 1) __stcs(reinterpret_cast<unsigned int*>(a.d_step_count) + g, c1);
-    else __stcs(reinterpret_cast<uint4*>(a.d_step_count) + g, make_uint4(cntw[0], cntw[1], cntw[2], cntw[3]));
-    __stcs(reinterpret_cast<float4*>(a.d_reward) + g, make_float4(rew[0], rew[1], rew[2], rew[3]));
-    if (a.d_done) __stcs(reinterpret_cast<unsigned int*>(a.d_done + e0), done1);
-    if (a.d_flags) __stcs(reinterpret_cast<unsigned int*>(a.d_flags + e0), flags4);
+    if constexpr (CW == 1) TS_ST(reinterpret_cast<unsigned int*>(a.d_step_count) + g, c1);
+    else TS_ST(reinterpret_cast<uint4*>(a.d_step_count) + g, make_uint4(cntw[0], cntw[1], cntw[2], cntw[3]));
+    TS_ST(reinterpret_cast<float4*>(a.d_reward) + g, make_float4(rew[0], rew[1], rew[2], rew[3]));
+    if (a.d_done) TS_ST(reinterpret_cast<unsigned int*>(a.d_done + e0), done1);
+    if (a.d_flags) TS_ST(reinterpret_cast<unsigned int*>(a.d_flags + e0), flags4);
 }
 
 // fill the per-block table of direction parameters (threads 0..3) -- call before any early return
@@ -213,16 +213,16 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     in.walls.load(a.d_walls, cap, g);
     if constexpr (GOAL == TS_GOAL_ORDERED) ld_words<PW>(a.d_targets_packed + e0 * PW, in.traw);
     else in.tboard.load(a.d_targets_packed, cap, g);
-    in.act4 = __ldcs(reinterpret_cast<const unsigned int*>(a.d_actions + e0));
+    in.act4 = TS_LD(reinterpret_cast<const unsigned int*>(a.d_actions + e0));
     in.cnt4 = 0;
     if constexpr (CW == 1) {
-        in.cnt4 = __ldcs(reinterpret_cast<const unsigned int*>(a.d_step_count) + g);
+        in.cnt4 = TS_LD(reinterpret_cast<const unsigned int*>(a.d_step_count) + g);
     } else {
-        const uint4 c = __ldcs(reinterpret_cast<const uint4*>(a.d_step_count) + g);
+        const uint4 c = TS_LD(reinterpret_cast<const uint4*>(a.d_step_count) + g);
         in.cntw[0] = c.x; in.cntw[1] = c.y; in.cntw[2] = c.z; in.cntw[3] = c.w;
     }
     in.prev_flags = 0;
-    if constexpr (!AR) in.prev_flags = __ldcs(reinterpret_cast<const unsigned int*>(a.d_flags + e0));
+    if constexpr (!AR) in.prev_flags = TS_LD(reinterpret_cast<const unsigned int*>(a.d_flags + e0));
     step_group<S, T, GOAL, AR, CW>(a, g, in, dir_tab);
 }
 
