@@ -96,6 +96,9 @@ SHAPES = [  # S, T, W, multi, N, K, max_steps
     (16, 8, 60, True, 2048, 64, 300),
     (16, 5, 100, False, 2048, 64, 100),
     (13, 1, 40, False, 2048, 64, 100),
+    (5, 2, 3, True, 1021, 300, 255),       # widest 1-byte step counter; N not a multiple of 4
+    (5, 2, 3, False, 1023, 300, 256),      # first 4-byte step counter
+    (6, 4, 8, True, 777, 40, 1),           # every step times out
 ]
 
 
@@ -372,6 +375,33 @@ def test_real_levels_step_parity(ts):
             assert np.array_equal(r.cpu().numpy(), want["reward"][k])
         total += n * K
     assert total == 400 * 96
+
+
+def test_side_stream_and_unaligned_action_views(ts):
+    """Calls follow torch's current stream, and an action tensor that cannot be handed to the
+    kernel as it is (odd offset view, int64 dtype, host tensor) is staged, not rejected."""
+    S, T, W, N, K = 6, 4, 8, 5000, 12
+    ref = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=21, auto_reset=True)
+    env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, True, seed=21, auto_reset=True)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 4, (K, ref.capacity), dtype=torch.uint8, device="cuda", generator=g)
+    pad = torch.zeros(N + 7, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    for k in range(K):
+        ref.step(acts[k])
+        kind = k % 3
+        if kind == 0:
+            pad[3:3 + N] = acts[k, :N]
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                env.step(pad[3:3 + N])                       # misaligned device view, side stream
+            torch.cuda.current_stream().wait_stream(side)
+        elif kind == 1:
+            env.step(acts[k, :N].to(torch.int64))            # wrong dtype
+        else:
+            env.step(acts[k, :N].cpu().numpy())              # host array
+        assert torch.equal(env.pos, ref.pos) and torch.equal(env.flags, ref.flags)
+        assert torch.equal(env.reward, ref.reward) and torch.equal(env.step_count, ref.step_count)
 
 
 def test_cuda_graph_replay_matches_eager(ts):
