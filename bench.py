@@ -159,7 +159,19 @@ def parity_check(ts, dev, n_envs: int = 8192, steps: int = 128) -> dict:
         bad += int((post.cpu().numpy() != want["pos"][k]).any(axis=(1, 2)).sum())
         bad += int((env.flags.cpu().numpy() != want["flags"][k]).sum())
         bad += int((r.cpu().numpy() != want["reward"][k]).sum())
-    return {"env_steps_checked": n_envs * steps, "mismatches": bad, "fields": "positions, flags (done/won/invalid/timeout), reward",
+    # K3 / valid-move mask of the states the rollout ended in (first n_obs envs), against the oracle
+    n_obs = min(n_envs, 1024)
+    obs = env.observe()[:n_obs].cpu().numpy()
+    valid = env.valid_moves()[:n_obs].cpu().numpy()
+    blocked_rc = [np.argwhere(b.reshape(S, S)) for b in blocked[:n_obs]]
+    obs_bad = 0
+    for i in range(n_obs):
+        st = orc.OracleState(S, blocked_rc[i], want["final_pos"][i], targets[i], MULTI)
+        obs_bad += int((st.get_state_array() != obs[i]).any())
+        obs_bad += int(sum(1 << d for d in st.valid_moves()) != int(valid[i]))
+    return {"env_steps_checked": n_envs * steps, "mismatches": bad,
+            "fields": "positions, flags (done/won/invalid/timeout), reward",
+            "observations_checked": n_obs, "observation_or_valid_mask_mismatches": obs_bad,
             "checker": "oracle/ts_oracle.c"}
 
 

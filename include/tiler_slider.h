@@ -35,10 +35,13 @@
  *    per env.  S <= 6: BS = PS = S+1 and a WALL board also has column S of every row and all
  *    bits past the last row set (sentinels that end a slide; ts_encode / ts_synth write
  *    them).  S = 7, 8: BS = S, PS = 16, no sentinels.
- *  - wide boards (S >= 9): walls = u16 [axis][capacity][16 lines]: plane 1 = rows (bit c of
- *    line r), used by LEFT/RIGHT, plane 0 = columns (bit r of line c), used by UP/DOWN; for
- *    S <= 15 bit S of every line is set as an edge sentinel; 64 bytes per env of which a step
- *    reads one 32-byte sector.  Set-goal target board = u16 [capacity][16 rows].  PS = 16.
+ *  - wide boards (S >= 9): walls = u16 [axis][capacity][L lines], L = S rounded up to even:
+ *    plane 1 = rows (line r, one bit per column), used by LEFT/RIGHT, plane 0 = columns (line
+ *    c, one bit per row), used by UP/DOWN; ts_walls_bytes(S) = 4*L bytes per env, of which a
+ *    step reads the 2*L bytes of one axis.  S <= 14: cell k of a
+ *    line is bit k+1, and bit 0 and bit S+1 of every line are set (edge sentinels); S = 15, 16:
+ *    cell k is bit k, no sentinel.  Set-goal target board = u16 [capacity][16 rows], cell
+ *    (r,c) = bit c of line r.  PS = 16.
  */
 #ifndef TILER_SLIDER_H
 #define TILER_SLIDER_H

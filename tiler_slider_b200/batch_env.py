@@ -355,12 +355,14 @@ class BatchedTilerSliderEnv:
         ps = self.pos_stride
         return torch.stack((p // ps, p % ps), dim=-1)
 
-    def _board_cells(self, buf: torch.Tensor) -> torch.Tensor:
+    def _board_cells(self, buf: torch.Tensor, walls: bool = False) -> torch.Tensor:
         """Unpack a plane-layout bitboard buffer to bool[N, S*S] (load-time / debugging aid)."""
         nb, cap, n = self.board_bytes, self.capacity, self.n_envs
-        if self.wide:   # u16 lines: walls [axis][capacity][16] (last plane = rows, bit c), targets [capacity][16]
-            lines = buf.view(torch.int16).view(-1, cap, 16)[-1, :n].to(torch.int32) & 0xFFFF
-            bits = (lines.unsqueeze(-1) >> torch.arange(16, device=buf.device)) & 1
+        if self.wide:   # u16 lines: walls [axis][capacity][S rounded up to even] (last plane = rows), targets [capacity][16]
+            per_env = (self.size + 1) // 2 * 2 if walls else 16
+            lines = buf.view(torch.int16).view(-1, cap, per_env)[-1, :n].to(torch.int32) & 0xFFFF
+            lead = 1 if walls and self.size <= 14 else 0     # wall lines of S <= 14 start with an edge sentinel
+            bits = (lines.unsqueeze(-1) >> (torch.arange(16, device=buf.device) + lead)) & 1
             return bits[:, : self.size, : self.size].reshape(n, self.size * self.size).bool()
         cols = []
         for k in range(self._lib.ts_plane_count(nb)):
@@ -372,7 +374,7 @@ class BatchedTilerSliderEnv:
         return bits.reshape(n, nb * 8)[:, : S * bs].reshape(n, S, bs)[:, :, :S].reshape(n, S * S).bool()
 
     def blocked_cells(self) -> torch.Tensor:
-        return self._board_cells(self._walls)
+        return self._board_cells(self._walls, walls=True)
 
     def target_positions(self) -> torch.Tensor:
         """Ordered mode: uint8[N,T,2].  Set mode: bool[N,S*S] target cells."""

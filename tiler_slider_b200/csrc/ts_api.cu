@@ -74,15 +74,17 @@ __device__ __forceinline__ int wall_bit(const uint8_t* blocked_cells, int S, int
 // Write the wall board(s) of one env from a 0/1 cell map (all three board classes).
 __device__ void store_walls(uint8_t* d_walls, size_t cap, size_t env, int S, const uint8_t* cellmap) {
     if (wide_board(S)) {
-        uint16_t* w = reinterpret_cast<uint16_t*>(d_walls) + env * 16;   // [axis][env][line]
-        const size_t plane = cap * 16;
-        for (int l = 0; l < 16; ++l) {
+        const int lines = 2 * wide_line_words(S);      // S rounded up to even
+        uint16_t* w = reinterpret_cast<uint16_t*>(d_walls) + env * lines;   // [axis][env][line]
+        const size_t plane = cap * lines;
+        const int lead = wide_line_lead(S);           // S <= 14: cells at bits 1..S between two sentinels
+        for (int l = 0; l < lines; ++l) {
             uint32_t col = 0, row = 0;
-            if (l < S && S < 16) col = row = 1u << S;   // edge sentinel (ts_wide.cu)
+            if (l < S && lead) col = row = 1u | (1u << (S + 1));   // edge sentinels (ts_wide.cu)
             if (l < S)
                 for (int k = 0; k < S; ++k) {
-                    if (cellmap[k * S + l]) col |= 1u << k;    // column l, bit = row
-                    if (cellmap[l * S + k]) row |= 1u << k;    // row l, bit = column
+                    if (cellmap[k * S + l]) col |= 1u << (k + lead);    // column l, bit = row
+                    if (cellmap[l * S + k]) row |= 1u << (k + lead);    // row l, bit = column
                 }
             w[0 * plane + l] = (uint16_t)col;
             w[1 * plane + l] = (uint16_t)row;

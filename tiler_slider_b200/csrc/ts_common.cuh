@@ -17,7 +17,7 @@
 //                   indices stops there without any per-tile edge test.  Target boards (set
 //                   goal) use the same stride without sentinels.
 //   S = 7, 8 (compact boards): BS = S, PS = 16, no sentinels.
-//   S >= 9 (wide boards): PS = 16; walls are two 32-byte sectors per env, rows and columns
+//   S >= 9 (wide boards): PS = 16; walls are two records of 4*ceil(S/2) bytes per env, rows and columns
 //                   (walls[axis][env][line] u16), the set-goal target board one sector
 //                   (tboard[env][row] u16); see ts_wide.cu.
 //   capacity        allocation stride in envs, a multiple of 128 so that every plane start and
@@ -44,7 +44,12 @@ __host__ __device__ constexpr int board_bits(int S) { return S * board_stride(S)
 __host__ __device__ constexpr int board_bytes(int S) { return (board_bits(S) + 7) / 8; }
 // wide boards (S >= 9) do not fit 64 bits: env-major sectors of sixteen 16-bit lines, see ts_wide.cu
 __host__ __device__ constexpr bool wide_board(int S) { return S > 8; }
-__host__ __device__ constexpr int walls_bytes(int S) { return wide_board(S) ? 64 : board_bytes(S); }        // per env
+// wide WALL lines: 9 <= S <= 14 keep cell k at bit k+1, between edge sentinels at bit 0 and bit S+1;
+// S = 15, 16 have no room: cell k at bit k, no sentinel
+__host__ __device__ constexpr int wide_line_lead(int S) { return S <= 14 ? 1 : 0; }
+// wide WALL records: ceil(S/2) pair words (two 16-bit lines each) per env and axis, two axis planes
+__host__ __device__ constexpr int wide_line_words(int S) { return (S + 1) / 2; }
+__host__ __device__ constexpr int walls_bytes(int S) { return wide_board(S) ? 8 * wide_line_words(S) : board_bytes(S); }   // per env
 __host__ __device__ constexpr int target_board_bytes(int S) { return wide_board(S) ? 32 : board_bytes(S); }  // per env, set goal
 
 // decomposition of nb bytes into planes of width 16 (repeated), 8, 4, 2, 1

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_a
         const size_t env = (size_t)(a.first_env + env0 + e);
         bool wall, tgt = false;
         if constexpr (wide_board(S)) {
-            wall = (reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * 16 + r] >> c) & 1;   // plane 1 = rows
+            wall = (reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * (2 * wide_line_words(S)) + r] >> (c + wide_line_lead(S))) & 1;   // plane 1 = rows
             if (!ordered) tgt = (reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * 16 + r] >> c) & 1;
         } else {
             const int bit = r * board_stride(S) + c;

@@ -6,17 +6,24 @@
 // 119-143), reset (environment.py:89-97), get_valid_moves (environment.py:149-171).
 //
 // A wide board does not fit a 64-bit word, so the bitboard tricks of ts_common.cuh do not
-// apply.  Layout (one 32-byte sector per env and axis, axis-major planes):
-//   walls[x][env][line]  u16, x = axis: plane 1 holds the rows (bit c of line r = cell (r,c)
-//                        blocked) and serves LEFT/RIGHT, plane 0 holds the columns (bit r of
-//                        line c) and serves UP/DOWN.  A step reads exactly ONE 32-byte sector
-//                        (select-source load); for UP/LEFT its lines are reversed in registers
-//                        so that every slide goes toward higher bits.  For S <= 15 bit S of every
-//                        line is stored as 1 (edge sentinel).
-//                        History (profiles/): with [env][4 orientations] DRAM fetched the whole
-//                        128-byte line around each sector (612 MB read per 4.2M-env launch instead
-//                        of 210 MB); four orientation planes cut that by a quarter, two axis
-//                        planes + in-register reversal by half.
+// apply.  Layout (one record of ceil(S/2) pair words per env and axis, axis-major planes):
+//   walls[x][env][line]  u16, x = axis: plane 1 holds the rows (line r, cell (r,c) at bit c+1)
+//                        and serves LEFT/RIGHT, plane 0 holds the columns (line c, cell (r,c) at
+//                        bit r+1) and serves UP/DOWN.  A step reads exactly ONE record
+//                        (select-source load).  For S <= 14 every line carries an edge sentinel
+//                        at BOTH ends (bit 0 and bit S+1), so that for UP/LEFT one BREV of a
+//                        pair word (two lines) turns both lines around with a sentinel still
+//                        ahead of every slide; cells then sit at bit 14-c of the other half.
+//                        S = 15, 16 have no room for that: plain lines (cell at bit c, no
+//                        sentinel), reversed and re-aligned in registers (slide_wide16).
+//                        History (profiles/): DRAM serves these reads at 128-byte granularity.
+//                        With [env][4 orientations] of 32 bytes the whole 128-byte line around the
+//                        one sector a step needs was fetched (612 MB read per 4.2M-env launch
+//                        instead of 210 MB); four orientation planes cut that by a quarter, two
+//                        axis planes + in-register reversal by half -- and since neighbouring envs
+//                        pick their axis independently, nearly every line of BOTH planes is still
+//                        touched, so what counts is the footprint: records hold only the
+//                        ceil(S/2) pair words a board of this size has (24 bytes for 12x12).
 //   tboard[env][row]     u16 target cells (set goal only)
 //   position byte        row*16 + col
 // Thread = one env.  The 16 line words of the chosen orientation and the occupancy lines
@@ -51,20 +58,18 @@ template <int PW> __device__ __forceinline__ void st_pos(uint8_t* p, size_t env,
     else reinterpret_cast<uint2*>(p)[env] = make_uint2(q[0], q[1]);
 }
 
-// Fetch the env's 32-byte wall sector of the move's axis (plane 1 = rows for LEFT/RIGHT, plane 0 =
-// columns for UP/DOWN), turn it toward the move direction and park it in the thread's smem
-// column.  Stored lines run toward DOWN / RIGHT; for UP / LEFT (f = 1) every line is reversed
-// in registers: brev flips the pair word (both halves reversed and swapped), PRMT swaps the
-// halves back, a shift re-aligns the S cells and the edge sentinel (bit S, S <= 15) is put back.
+// S = 15, 16 (plain lines, 8 pair words).  Fetch the env's 32-byte wall record of the move's axis (plane 1 =
+// rows for LEFT/RIGHT, plane 0 = columns for UP/DOWN), turn it toward the move direction and park
+// it in the thread's smem column.  Stored lines run toward DOWN / RIGHT; for UP / LEFT (f = 1)
+// every line is reversed in registers: brev flips the pair word (both halves reversed and
+// swapped), PRMT swaps the halves back, a shift re-aligns the S cells.
 __device__ __forceinline__ void load_oriented_walls(WideSmem& sm, const uint4* sector, int S, uint32_t f) {
     const uint4 b0 = __ldg(sector), b1 = __ldg(sector + 1);
     uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     if (f) {
         const uint32_t cells2 = ((1u << S) - 1u) * 0x00010001u;          // the S cell bits of both halves
-        const uint32_t sent2 = S < 16 ? (1u << S) * 0x00010001u : 0u;    // edge sentinels
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            w[k] = ((__byte_perm(__brev(w[k]), 0, 0x1032) >> (16 - S)) & cells2) | sent2;
+        for (int k = 0; k < 8; ++k) w[k] = (__byte_perm(__brev(w[k]), 0, 0x1032) >> (16 - S)) & cells2;
     }
     uint32_t* wcol = &sm.w[0][threadIdx.x];
 #pragma unroll
@@ -75,8 +80,8 @@ __device__ __forceinline__ uint32_t half_of(uint32_t word, uint32_t half) {
     return __byte_perm(word, 0, 0x4410u + half * 0x22u);   // half ? word >> 16 : word & 0xffff
 }
 
-// One slide of all T tiles of the calling thread's env, S == 16 (no room for a stored sentinel in
-// a 16-bit line: lines are extracted and the edge bit is OR-ed in).  `board` = the 32-byte
+// One slide of all T tiles of the calling thread's env, S = 15 or 16 (no room for two stored
+// sentinels in a 16-bit line: lines are extracted and the edge bit is OR-ed in).  `board` = the 32-byte
 // orientation sector for `action`.  q: position bytes (row*16+col), updated in place.
 template <int T>
 __device__ __forceinline__ void slide_wide16(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
@@ -123,50 +128,78 @@ __device__ __forceinline__ void slide_wide16(WideSmem& sm, uint32_t (&q)[(T + 3)
     if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
 }
 
-// One slide, 9 <= S <= 15: every stored line word carries its edge sentinel at bit S, so a pair
-// word (two 16-bit lines) is used as it is -- shifting it right by 16*(line&1) + offset + 1
-// leaves exactly the cells past the tile, and the scan stops at the line's own sentinel before
-// it can reach the neighbouring line's bits.  That shift amount is the low 5 bits of the byte
-// (line<<4 | offset), plus one.
-template <int T>
-__device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint4* board, int S, uint32_t action) {
+// One slide, 9 <= S <= 14.  Every stored line has its cells at bits 1..S between two edge
+// sentinels (bit 0, bit S+1), two lines per 32-bit pair word.  DOWN / RIGHT use the words as they
+// are: a tile at offset c of line l is bit 16*(l&1) + c+1 of pair l>>1.  UP / LEFT use BREV of
+// the words: the same tile is then bit 16*(1-(l&1)) + 14-c, and the line's bit-0 sentinel has
+// become the bit-15 sentinel ahead of it.  Either way "bit index within the pair" is the low 5
+// bits of the byte b = l*16 + off (bit 4 flipped for UP / LEFT), which is what the funnel shifts
+// consume directly, and the slide is: x = walls >> b has the tile's own (wall-free) cell at bit 0
+// and the first wall or sentinel ahead as its lowest set bit; (x-1) & ~x are the cells up to
+// there; those not occupied (the tile itself is occupied) are the empty cells it moves over.
+template <int T, int LW>
+__device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) / 4], const uint32_t* rec, uint32_t action) {
     constexpr int PR = (T + 3) / 4;
     const uint32_t h = (action >> 1) & 1u, f = ~action & 1u;
-    load_oriented_walls(sm, board, S, f);
     uint32_t* wcol = &sm.w[0][threadIdx.x];     // this thread's column: pair k at wcol[k * WIDE_THREADS]
     uint32_t* ocol = &sm.o[0][threadIdx.x];
+    {
+        uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // LW = 5..7 pair words; records are 4*LW bytes apart
+        if constexpr (LW % 2 == 0) {            // 8-byte aligned records
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ocol[k * WIDE_THREADS] = 0;
-
-    // line / offset nibbles of every tile; offsets flipped for UP/LEFT with one multiply-add
-    const uint32_t fm = 1u - 2u * f, fk = f * (0x01010101u * (uint32_t)(S - 1));
-    uint32_t LN[PR], OF[PR], B[PR], ACC[PR];
+            for (int k = 0; k < LW / 2; ++k) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(rec) + k);
+                w[2 * k] = v.x;
+                w[2 * k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < LW; ++k) w[k] = __ldg(rec + k);
+        }
+        const uint32_t fmask = 0u - f;
+#pragma unroll
+        for (int k = 0; k < LW; ++k) {          // pairs >= LW hold no line of the board
+            uint32_t r;
+            asm("brev.b32 %0, %1;" : "=r"(r) : "r"(w[k]));
+            wcol[k * WIDE_THREADS] = w[k] ^ ((w[k] ^ r) & fmask);   // f ? r : w[k] as one LOP3
+            ocol[k * WIDE_THREADS] = 0;
+        }
+    }
+    // offset of every tile toward the move direction: c+1, or 14-c for UP / LEFT (SWAR, one
+    // multiply-add: bytes stay in 1..14, so nothing carries)
+    const uint32_t fm = 1u - 2u * f;
+    const uint32_t fk = 0x01010101u + f * 0x0D0D0D0Du;        // +1 | 14
+    const uint32_t fu = 0xFEFEFEFFu + f * 0x0F0F0F0Fu;        // -1 | 14 : off -> c on the way back
+    const uint32_t fx = f * 0x10101010u;                      // BREV swapped the two lines of a pair
+    uint32_t LN[PR], OF[PR], B[PR], PM[PR], ACC[PR];
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
         const uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu, lo = q[w] & 0x0F0F0F0Fu;   // rows, cols
         LN[w] = h ? hi : lo;
         OF[w] = (h ? lo : hi) * fm + fk;
-        B[w] = LN[w] * 16u + OF[w];
+        B[w] = (LN[w] * 16u + OF[w]) ^ fx;
+        PM[w] = B[w] & 0xE0E0E0E0u;                           // pair index * 32 per byte
         ACC[w] = 0;
     }
-    uint32_t pofs[T], sh[T];
+    uint32_t* oc[T];
+    uint32_t sh[T];
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        const uint32_t b = byte_of<i % 4>(B[i / 4]);
-        pofs[i] = (b >> 5) * WIDE_THREADS;           // pair index = line >> 1
-        sh[i] = b & 31u;                             // 16*(line&1) + offset
-        ocol[pofs[i]] |= 1u << sh[i];
+        sh[i] = B[i / 4] >> (8 * (i % 4));                    // funnel shifts read the low 5 bits
+        oc[i] = ocol + byte_of<i % 4>(PM[i / 4]) * (WIDE_THREADS / 32);
+        // 1 << (sh & 31) into the pair word; ATOMS.OR is one instruction where a read-modify-write
+        // is three (measured: 53.7 vs 55.0 us per 4.2M-env step), and nothing else touches the column
+        atomicOr(oc[i], __funnelshift_l(0u, 1u, sh[i]));
     });
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        const uint32_t x = (wcol[pofs[i]] >> sh[i]) >> 1;     // cells past the tile, sentinel included
-        const uint32_t y = (ocol[pofs[i]] >> sh[i]) >> 1;
-        const uint32_t run = (x - 1u) & ~x;                   // cells before the first wall / the edge
-        ACC[i / 4] = mad_u32((uint32_t)__popc(run & ~y), 1u << (8 * (i % 4)), ACC[i / 4]);
+        const uint32_t x = __funnelshift_r(*(oc[i] - 8 * WIDE_THREADS), 0u, sh[i]);   // the wall pair sits 8 rows below
+        const uint32_t y = __funnelshift_r(*oc[i], 0u, sh[i]);
+        ACC[i / 4] = mad_u32((uint32_t)__popc((x - 1u) & ~x & ~y), 1u << (8 * (i % 4)), ACC[i / 4]);
     });
 #pragma unroll
     for (int w = 0; w < PR; ++w) {
-        const uint32_t ofn = (OF[w] + ACC[w]) * fm + fk;      // new offset, un-flipped
+        const uint32_t ofn = (OF[w] + ACC[w]) * fm + fu;      // new column / row
         q[w] = (h ? LN[w] : ofn) * 16u + (h ? ofn : LN[w]);
     }
     if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
@@ -186,9 +219,10 @@ __device__ __forceinline__ bool on_targets_wide(const uint32_t (&q)[(T + 3) / 4]
     return all;
 }
 
-// AR: auto-reset on / off (off: finished envs are frozen and report STALE); S16: board size 16
-// (lines without a stored sentinel).  32-bit env index: ts_step rejects larger batches.
-template <int T, int GOAL, bool AR, bool S16>
+// AR: auto-reset on / off (off: finished envs are frozen and report STALE); LW = ceil(S/2) pair
+// words per wall record (8: board size 15 or 16, plain lines without stored sentinels).
+// 32-bit env index: ts_step rejects larger batches.
+template <int T, int GOAL, bool AR, int LW>
 __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kernel(const __grid_constant__ ts_step_args a) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
     __shared__ WideSmem sm;
@@ -207,9 +241,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kerne
     if constexpr (!AR) stale = (a.d_flags[env] & F_DONE) != 0;
     const float r_win = a.r_win, r_step = a.r_step, r_invalid = a.r_invalid;
 
-    const uint4* sector = reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * 2;
-    if constexpr (S16) slide_wide16<T>(sm, q, sector, 16, action);
-    else slide_wide<T>(sm, q, sector, a.size, action);
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.d_walls) + ((size_t)(action >> 1) * (size_t)a.capacity + env) * LW;
+    if constexpr (LW == 8) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(rec), a.size, action);
+    else slide_wide<T, LW>(sm, q, rec, action);
 
     bool moved = false, won = a.never_win == 0;
 #pragma unroll
@@ -266,8 +300,14 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_c
         uint32_t q[PR];
 #pragma unroll
         for (int w = 0; w < PR; ++w) q[w] = q0[w];
-        if (a.size == 16) slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * 2, a.size, d);
-        else slide_wide<T>(sm, q, reinterpret_cast<const uint4*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * 2, a.size, d);
+        const int lw = wide_line_words(a.size);
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * (size_t)lw;
+        switch (lw) {
+            case 5: slide_wide<T, 5>(sm, q, rec, d); break;
+            case 6: slide_wide<T, 6>(sm, q, rec, d); break;
+            case 7: slide_wide<T, 7>(sm, q, rec, d); break;
+            default: slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(rec), a.size, d); break;
+        }
         bool moved = false;
 #pragma unroll
         for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
@@ -296,12 +336,17 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_goal_kernel(const __grid_co
     a.d_won[env] = won ? 1 : 0;
 }
 
+template <int T, int GOAL, int LW> static void launch_wide_step_lw(const ts_step_args& a, unsigned blocks, cudaStream_t st) {
+    if (a.auto_reset != 0) wide_step_kernel<T, GOAL, true, LW><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    else wide_step_kernel<T, GOAL, false, LW><<<blocks, WIDE_THREADS, 0, st>>>(a);
+}
 template <int T, int GOAL> static void launch_wide_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t st) {
-    const bool ar = a.auto_reset != 0, s16 = a.size == 16;
-    if (ar && !s16) wide_step_kernel<T, GOAL, true, false><<<blocks, WIDE_THREADS, 0, st>>>(a);
-    else if (ar) wide_step_kernel<T, GOAL, true, true><<<blocks, WIDE_THREADS, 0, st>>>(a);
-    else if (!s16) wide_step_kernel<T, GOAL, false, false><<<blocks, WIDE_THREADS, 0, st>>>(a);
-    else wide_step_kernel<T, GOAL, false, true><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    switch (wide_line_words(a.size)) {
+        case 5: launch_wide_step_lw<T, GOAL, 5>(a, blocks, st); break;
+        case 6: launch_wide_step_lw<T, GOAL, 6>(a, blocks, st); break;
+        case 7: launch_wide_step_lw<T, GOAL, 7>(a, blocks, st); break;
+        default: launch_wide_step_lw<T, GOAL, 8>(a, blocks, st); break;
+    }
 }
 template <int T> static cudaError_t launch_wide_step(const ts_step_args& a, cudaStream_t st) {
     if (a.first_env + a.n_envs >= ((int64_t)1 << 32)) return cudaErrorInvalidValue;   // 32-bit env index
