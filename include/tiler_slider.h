@@ -250,6 +250,14 @@ typedef struct ts_bfs_args {
      * included) are also copied to d_won_keys, in the order of d_counts[1] */
     uint64_t *d_won_keys;
     int64_t won_capacity;
+    /* ts_bfs_hash_insert, optional per-puzzle tallies (puzzle id = key bits 32..62; 0 when
+     * n_tiles > 4): d_states_per_puzzle[pid] += 1 for every new key; for every goal successor
+     * d_solve_depth[pid] = min(itself, depth), and the first one to lower it also stores its key
+     * in d_goal_keys[pid] (optional) -- a goal state at the smallest depth */
+    int64_t *d_states_per_puzzle;
+    int32_t *d_solve_depth;
+    uint64_t *d_goal_keys;
+    int32_t depth, reserved2;
 } ts_bfs_args;
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
 int ts_bfs_expand(const ts_bfs_args *a, void *stream);

@@ -38,6 +38,7 @@ class OracleBfsKernels:
     def expand(self, frontier):
         out = []
         for key in frontier.tolist():
+            key &= 0x7FFFFFFFFFFFFFFF                       # the goal bit of an input key is ignored
             pid, st = (key >> 32) & 0x7FFFFFFF, None
             st = self.states[pid]
             cells = [(key >> (8 * i)) & 0xFF for i in range(st.n_tiles)]

@@ -74,7 +74,9 @@ class BfsArgs(C.Structure):
                 ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_in_keys", _vp),
                 ("d_out_keys", _vp), ("d_table", _vp), ("d_counts", _vp),
                 ("d_parent_keys", _vp), ("d_table_parent", _vp), ("d_moves", _vp), ("d_lengths", _vp),
-                ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64)]
+                ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64),
+                ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_goal_keys", _vp),
+                ("depth", _i32), ("reserved2", _i32)]
 
 
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)

@@ -169,29 +169,71 @@ __global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs
 // d_counts[2] is set when the table is full.
 __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args a) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.n_items) return;
-    const uint64_t raw = a.d_in_keys[i];
-    if (raw == BFS_NONE) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t raw = i < a.n_items ? a.d_in_keys[i] : BFS_NONE;
+    const bool live = raw != BFS_NONE;
     const uint64_t key = raw & ~BFS_WON_BIT;
-    if (raw & BFS_WON_BIT) {
-        const unsigned long long w = atomicAdd((unsigned long long*)&a.d_counts[1], 1ull);
-        if (a.d_won_keys && (int64_t)w < a.won_capacity) a.d_won_keys[w] = raw;
-    }
-    const uint64_t mask = (uint64_t)a.table_capacity - 1;
-    uint64_t slot = mix64(key) & mask;
-    for (int64_t probe = 0; probe < a.table_capacity; ++probe) {
-        const unsigned long long old = atomicCAS((unsigned long long*)&a.d_table[slot], (unsigned long long)BFS_NONE, (unsigned long long)key);
-        if (old == BFS_NONE) {
-            if (a.d_table_parent) a.d_table_parent[slot] = a.d_parent_keys ? (a.d_parent_keys[i >> 2] & ~BFS_WON_BIT) : BFS_NONE;
-            const unsigned long long pos = atomicAdd((unsigned long long*)&a.d_counts[0], 1ull);
-            if ((int64_t)pos < a.out_capacity) a.d_out_keys[pos] = raw;
-            else a.d_counts[2] = 1;
-            return;
+    bool is_new = false, full = false;
+    if (live) {
+        const uint64_t mask = (uint64_t)a.table_capacity - 1;
+        uint64_t slot = mix64(key) & mask;
+        int64_t probe = 0;
+        for (; probe < a.table_capacity; ++probe) {
+            // Three successors in four are revisits: look before you CAS.  A slot never changes once
+            // it holds a key, so a plain (L2) load that sees a key is final; one that sees EMPTY may
+            // be out of date, and the CAS that follows settles it.
+            unsigned long long old = __ldcg((const unsigned long long*)&a.d_table[slot]);
+            if (old == BFS_NONE)
+                old = atomicCAS((unsigned long long*)&a.d_table[slot], (unsigned long long)BFS_NONE, (unsigned long long)key);
+            else if (old != key) { slot = (slot + 1) & mask; continue; }
+            if (old == BFS_NONE) {
+                if (a.d_table_parent) a.d_table_parent[slot] = a.d_parent_keys ? (a.d_parent_keys[i >> 2] & ~BFS_WON_BIT) : BFS_NONE;
+                is_new = true;
+                break;
+            }
+            if (old == key) break;
+            slot = (slot + 1) & mask;
         }
-        if (old == key) return;
-        slot = (slot + 1) & mask;
+        full = probe == a.table_capacity;
     }
-    a.d_counts[2] = 1;
+    // one cursor bump per warp, not per key: a frontier of 1e8 new keys would otherwise queue
+    // 1e8 atomics on one address.  Keys of a warp stay in lane order in the output.
+    const bool won = live && (raw & BFS_WON_BIT) != 0;
+    const unsigned new_mask = __ballot_sync(0xFFFFFFFFu, is_new), won_mask = __ballot_sync(0xFFFFFFFFu, won);
+    if (new_mask) {
+        const int leader = __ffs(new_mask) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd((unsigned long long*)&a.d_counts[0], (unsigned long long)__popc(new_mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (is_new) {
+            const unsigned long long pos = base + (unsigned long long)__popc(new_mask & ((1u << lane) - 1u));
+            if ((int64_t)pos < a.out_capacity) a.d_out_keys[pos] = raw;
+            else full = true;
+        }
+    }
+    // optional per-puzzle tallies; a frontier is roughly in puzzle order, so the new keys of a warp
+    // mostly share a puzzle and one lane adds for all of them
+    const uint32_t pid = a.n_tiles <= 4 ? (uint32_t)(key >> 32) & 0x7FFFFFFFu : 0u;
+    if (a.d_states_per_puzzle && is_new) {
+        const unsigned peers = __match_any_sync(new_mask, pid);
+        if ((int)lane == __ffs(peers) - 1)
+            atomicAdd((unsigned long long*)&a.d_states_per_puzzle[pid], (unsigned long long)__popc(peers));
+    }
+    if (a.d_solve_depth && won) {
+        const int before = atomicMin(&a.d_solve_depth[pid], a.depth);
+        if (before > a.depth && a.d_goal_keys) a.d_goal_keys[pid] = raw;
+    }
+    if (won_mask) {
+        const int leader = __ffs(won_mask) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd((unsigned long long*)&a.d_counts[1], (unsigned long long)__popc(won_mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (won) {
+            const unsigned long long w = base + (unsigned long long)__popc(won_mask & ((1u << lane) - 1u));
+            if (a.d_won_keys && (int64_t)w < a.won_capacity) a.d_won_keys[w] = raw;
+        }
+    }
+    if (full) a.d_counts[2] = 1;
 }
 
 // slot of `key` in the visited table, or -1
