@@ -31,6 +31,8 @@ def main() -> int:
     ap.add_argument("--seed", type=int, default=1004)
     ap.add_argument("--table-log2", type=int, default=0, help="log2 of the per-rank visited-table capacity (0 = auto)")
     ap.add_argument("--check", type=int, default=8, help="puzzles cross-checked against the CPU oracle on rank 0")
+    ap.add_argument("--exchange", choices=["auto", "nccl", "p2p"], default="auto",
+                    help="multi-GPU: NCCL all-to-all, or the expand kernel writing into peer inboxes over NVLink")
     ap.add_argument("--profile", action="store_true", help="a third, phase-synchronised search: wall time per phase (rank 0)")
     args = ap.parse_args()
 
@@ -47,7 +49,7 @@ def main() -> int:
         dist.init_process_group("nccl", device_id=dev)
     table = ts.BatchedTilerSliderEnv.synthetic(args.puzzles, args.size, args.tiles, args.walls, True, seed=args.seed, device=dev)
     log2 = args.table_log2 or max(16, int(np.ceil(np.log2(args.puzzles * 16384 / world))))   # ~3,400 states per puzzle on average
-    solver = BfsSolver(table, table_capacity=1 << log2)
+    solver = BfsSolver(table, table_capacity=1 << log2, exchange=args.exchange)
     if world > 1:   # create the NCCL communicator and its all-to-all channels outside the timed region
         w = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_to_all_single(torch.empty_like(w), w)
@@ -86,7 +88,7 @@ def main() -> int:
     if rank == 0:
         solved = int((res.solve_depth_per_puzzle >= 0).sum())
         print(json.dumps({"config": f"BFS {args.puzzles} puzzles {args.size}x{args.size}/{args.tiles} tiles/{args.walls} walls, "
-                                    f"{world} GPU(s), table 2^{log2} per rank",
+                                    f"{world} GPU(s), table 2^{log2} per rank, exchange {solver.exchange if world > 1 else 'none'}",
                           "n_gpus": world, "unique_states": res.n_states, "generated_successors": res.generated,
                           "depth": len(res.levels) - 1, "seconds": dt, "seconds_cold": dt_cold,
                           "generated_successors_per_s": res.generated / dt, "unique_states_per_s": res.n_states / dt,

@@ -258,12 +258,27 @@ typedef struct ts_bfs_args {
     int32_t *d_solve_depth;
     uint64_t *d_goal_keys;
     int32_t depth, reserved2;
+    /* ts_bfs_expand_exchange (multi-GPU, peer memory): d_peer_bufs[r] = rank r's exchange buffer
+     * as mapped into THIS process (NVLink peer mapping, e.g. torch symmetric memory):
+     *   word 0, 1          arrival cursors of inbox 0 / inbox 1 (keys received so far)
+     *   word 2             set to 1 when an inbox overflowed
+     *   word TS_BFS_XHDR + p * inbox_capacity ...   inbox p (u64 keys)
+     * The successors of d_in_keys are written straight into inbox `parity` of their owner rank
+     * (hash(key) % n_ranks); d_counts[3] += number of keys sent. */
+    uint64_t *const *d_peer_bufs;
+    int64_t inbox_capacity;
+    int32_t parity, reserved3;
 } ts_bfs_args;
+#define TS_BFS_XHDR 16
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
 int ts_bfs_expand(const ts_bfs_args *a, void *stream);
 int ts_bfs_partition_count(const ts_bfs_args *a, void *stream);
 int ts_bfs_partition_scatter(const ts_bfs_args *a, void *stream);
 int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
+/* expand + bucket + exchange in one kernel: no partition pass, no size exchange, no all-to-all;
+ * the caller separates levels with any collective that orders the ranks' streams (an all-reduce
+ * of the sent counts doubles as the termination test) and alternates `parity` level by level. */
+int ts_bfs_expand_exchange(const ts_bfs_args *a, void *stream);
 int ts_bfs_traceback(const ts_bfs_args *a, void *stream);
 
 /* ---------------------------------------------------------------------------------------

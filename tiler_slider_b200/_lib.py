@@ -76,7 +76,8 @@ class BfsArgs(C.Structure):
                 ("d_parent_keys", _vp), ("d_table_parent", _vp), ("d_moves", _vp), ("d_lengths", _vp),
                 ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64),
                 ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_goal_keys", _vp),
-                ("depth", _i32), ("reserved2", _i32)]
+                ("depth", _i32), ("reserved2", _i32),
+                ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("reserved3", _i32)]
 
 
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
@@ -101,6 +102,7 @@ SYMBOLS = {
     "ts_goal_check": (C.c_int, [C.POINTER(GoalArgs), _vp]),
     "ts_bfs_seed": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_expand": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_expand_exchange": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_partition_count": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),

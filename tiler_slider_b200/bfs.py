@@ -131,6 +131,43 @@ class CudaBfsKernels:
     def new_table(self, capacity: int) -> torch.Tensor:
         return torch.full((capacity,), NONE, dtype=torch.int64, device=self.device)
 
+    # ---- exchange through NVLink peer memory (ts_bfs_expand_exchange) ----------------------
+    XHDR = 16                                   # TS_BFS_XHDR: header words ahead of the two inboxes
+
+    def setup_peer_exchange(self, group, inbox_capacity: int) -> bool:
+        """Allocate this rank's exchange buffer (two inboxes + cursors) in symmetric memory and
+        map every peer's buffer (torch.distributed._symmetric_memory: CUDA VMM handles over
+        NVLink).  Returns False when peer mapping is not available; the caller then keeps the
+        NCCL all-to-all path."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = group if group is not None else dist.group.WORLD
+            buf = symm.empty(self.XHDR + 2 * inbox_capacity, dtype=torch.int64, device=self.device)
+            hdl = symm.rendezvous(buf, group)
+        except Exception as e:                  # no peer access / no fabric handles
+            self.peer_exchange_error = repr(e)
+            return False
+        buf[: self.XHDR].zero_()
+        self._xbuf, self._xhdl, self._xcap = buf, hdl, int(inbox_capacity)
+        self._xpeers = torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self._xworld = len(hdl.buffer_ptrs)
+        self._xcounts = torch.zeros(4, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        hdl.barrier()                           # every header is zero before anyone sends
+        return True
+
+    def expand_exchange(self, frontier: torch.Tensor, parity: int) -> None:
+        """K4x: successors of `frontier` go straight into inbox `parity` of their owner ranks;
+        self._xcounts[3] accumulates the number of keys this rank sent."""
+        a = self._args(n_items=frontier.numel(), n_ranks=self._xworld, d_in_keys=frontier.data_ptr(),
+                       d_counts=self._xcounts.data_ptr(), d_peer_bufs=self._xpeers.data_ptr(),
+                       inbox_capacity=self._xcap, parity=parity)
+        self._call(self.lib.ts_bfs_expand_exchange, a, "ts_bfs_expand_exchange")
+
+    def inbox(self, parity: int, n: int) -> torch.Tensor:
+        o = self.XHDR + parity * self._xcap
+        return self._xbuf[o: o + n]
+
     def insert(self, table: torch.Tensor, keys: torch.Tensor, parents: torch.Tensor | None = None,
                parent_table: torch.Tensor | None = None, stats: "BfsStats | None" = None) -> tuple[torch.Tensor, int]:
         """Insert keys; returns (keys that were new, with their goal bit; #goal successors seen).
@@ -181,7 +218,8 @@ class BfsSolver:
     """Level-synchronous BFS over a batch of puzzles, hash-partitioned over the ranks of `group`."""
 
     def __init__(self, puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv | None = None, *, table_capacity: int = 1 << 22,
-                 device="cuda", group=None, kernels=None, n_puzzles: int | None = None, profile: bool = False):
+                 device="cuda", group=None, kernels=None, n_puzzles: int | None = None, profile: bool = False,
+                 exchange: str = "auto"):
         if kernels is None:
             table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else \
                 BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
@@ -195,6 +233,20 @@ class BfsSolver:
         if table_capacity & (table_capacity - 1):
             raise ValueError("table_capacity must be a power of two")
         self.table_capacity = table_capacity
+        # how successors reach their owner rank: "nccl" = bucket + all_to_all_single; "p2p" = the
+        # expand kernel writes them into the owners' inboxes through NVLink peer memory; "auto" =
+        # p2p when the peer mapping can be set up
+        if exchange not in ("auto", "nccl", "p2p"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'p2p'")
+        self.exchange = "nccl"
+        if self.world > 1 and exchange != "nccl" and isinstance(self.k, CudaBfsKernels):
+            ok = self.k.setup_peer_exchange(group, max(1 << 20, table_capacity // 2))
+            flag = torch.tensor([int(ok)], device=self.k.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # all ranks or none
+            if int(flag.item()):
+                self.exchange = "p2p"
+            elif exchange == "p2p":
+                raise RuntimeError(f"peer-memory exchange unavailable: {getattr(self.k, 'peer_exchange_error', 'a peer failed')}")
         self.profile = profile          # synchronise after every phase and sum wall time per phase into self.phase_seconds
         self.phase_seconds: dict[str, float] = {}
 
@@ -231,6 +283,21 @@ class BfsSolver:
         recv = ws("recv", sum(rs)) if ws else torch.empty(sum(rs), dtype=torch.int64, device=send.device)
         self._timed("all_to_all", lambda: dist.all_to_all_single(recv, send, rs, sizes, group=self.group))
         return recv, True
+
+    def _peer_level(self, parents: torch.Tensor, parity: int) -> tuple[torch.Tensor, bool]:
+        """One level of the peer-memory exchange: K4x, then one all-reduce of the sent counts --
+        it orders the ranks (every rank's K4x is complete, so every inbox is) and tells whether
+        anything is left anywhere -- then this rank's arrivals are read from its own inbox."""
+        k = self.k
+        k._xcounts.zero_()
+        k.expand_exchange(parents, parity)
+        sent = k._xcounts[3:4].clone()
+        dist.all_reduce(sent, group=self.group)
+        n_sent, n_in, overflow = torch.cat([sent, k._xbuf[parity: parity + 1], k._xbuf[2:3] + k._xcounts[2:3]]).tolist()
+        if overflow:
+            raise RuntimeError("BFS exchange inbox is full: raise table_capacity")
+        k._xbuf[parity: parity + 1].zero_()        # nobody writes this inbox again before the level after next
+        return k.inbox(parity, n_in), bool(n_sent)
 
     def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
         """Search every puzzle to exhaustion (or max_depth).  with_paths (single rank only): also
@@ -276,14 +343,17 @@ class BfsSolver:
         depth = 0
         while depth < max_depth:
             parents = frontier                                # expand / insert ignore the goal bit of their inputs
-            succ = self._timed("expand", k.expand, parents)
-            # single rank: successors go straight to the table (it skips NONE) and successor i stays
-            # next to its parent i // 4; several ranks: bucket by owner and exchange
-            recv, alive = self._exchange(succ)
+            if self.exchange == "p2p":
+                recv, alive = self._timed("expand_exchange", self._peer_level, parents, depth & 1)
+            else:
+                succ = self._timed("expand", k.expand, parents)
+                # single rank: successors go straight to the table (it skips NONE) and successor i stays
+                # next to its parent i // 4; several ranks: bucket by owner and exchange
+                recv, alive = self._exchange(succ)
             if not alive:
                 break
             depth += 1
-            generated += succ.numel()
+            generated += 4 * parents.numel()
             frontier, n_won = self._timed("insert", insert, recv, parents, depth)
             if per_puzzle and n_won and stats is None:
                 won = getattr(k, "last_won", None)

@@ -69,15 +69,13 @@ __global__ void __launch_bounds__(256) bfs_seed_kernel(const ts_bfs_args a) {
     a.d_out_keys[i] = make_key<T>(q, (uint64_t)i);
 }
 
-// K4: thread = one frontier state, four successors
+// the four successor keys of one frontier key (TS_BFS_NONE where the move changed nothing)
 template <int S, int T>
-__global__ void __launch_bounds__(256) bfs_expand_kernel(const ts_bfs_args a) {
+__device__ __forceinline__ void successors(const ts_bfs_args& a, uint64_t in_key, uint64_t (&out)[4]) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4, NB = board_bytes(S);
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.n_items) return;
     uint32_t q0[PR];
     uint64_t pid;
-    split_key<T>(a.d_in_keys[i], q0, pid);
+    split_key<T>(in_key, q0, pid);
     const size_t cap = (size_t)a.puzzle_capacity;
     const uint64_t walls = load_board_elem<NB>(a.d_walls, cap, (size_t)pid);
     uint64_t tboard = 0;
@@ -106,8 +104,19 @@ __global__ void __launch_bounds__(256) bfs_expand_kernel(const ts_bfs_args a) {
         for (int w = 0; w < PR; ++w) same &= q[w] == q0[w];
         uint64_t key = make_key<T>(q, pid) | (won ? BFS_WON_BIT : 0ull);
         if (same && !won) key = BFS_NONE;
-        a.d_out_keys[4 * i + d] = key;
+        out[d] = key;
     }
+}
+
+// K4: thread = one frontier state, four successors
+template <int S, int T>
+__global__ void __launch_bounds__(256) bfs_expand_kernel(const ts_bfs_args a) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_items) return;
+    uint64_t key[4];
+    successors<S, T>(a, a.d_in_keys[i], key);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) a.d_out_keys[4 * i + d] = key[d];
 }
 
 // owner rank of a key (won bit excluded)
@@ -162,6 +171,56 @@ __global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs
         base[threadIdx.x] = atomicAdd((unsigned long long*)&a.d_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
     __syncthreads();
     if (live) a.d_out_keys[base[owner] + slot] = key;
+}
+
+// K4x: expand + bucket + exchange over NVLink peer memory in one kernel.  A block keeps its 1024
+// successors in registers, builds the per-owner histogram in shared memory (warp-aggregated),
+// reserves its share of every owner's inbox with ONE system-scope atomic per owner on that rank's
+// arrival cursor, and stores the keys straight into the owners' inboxes -- for a remote owner
+// these are posted writes through the NVLink mapping.  No partition pass over the successors, no
+// size exchange, no all-to-all; nothing here waits on another GPU.
+template <int S, int T>
+__global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_args a) {
+    __shared__ unsigned int hist[64];
+    __shared__ unsigned long long base[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    uint64_t key[4] = {BFS_NONE, BFS_NONE, BFS_NONE, BFS_NONE};
+    if (i < a.n_items) successors<S, T>(a, a.d_in_keys[i], key);
+    uint32_t owner[4], slot[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const bool live = key[d] != BFS_NONE;
+        owner[d] = live ? key_owner(key[d], (uint32_t)a.n_ranks) : 0u;
+        slot[d] = block_bucket_slot(hist, live, owner[d]);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.n_ranks) {
+        const unsigned n = hist[threadIdx.x];
+        unsigned long long b = ~0ull;
+        if (n) {
+            uint64_t* peer = a.d_peer_bufs[threadIdx.x];
+            b = atomicAdd_system((unsigned long long*)(peer + a.parity), (unsigned long long)n);
+            if (b + n > (unsigned long long)a.inbox_capacity) {      // inbox full: drop and report
+                peer[2] = 1;
+                a.d_counts[2] = 1;
+                b = ~0ull;
+            }
+            atomicAdd((unsigned long long*)&a.d_counts[3], (unsigned long long)n);
+        }
+        base[threadIdx.x] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        if (key[d] == BFS_NONE) continue;
+        const unsigned long long b = base[owner[d]];
+        if (b == ~0ull) continue;
+        uint64_t* inbox = a.d_peer_bufs[owner[d]] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
+        inbox[b + slot[d]] = key[d];
+    }
+    __threadfence_system();
 }
 
 // K5: insert keys into the open-addressing visited table (EMPTY = all ones).  New keys are
@@ -296,6 +355,7 @@ template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a,
     case T:                                                                             \
         if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
         else if (op == 1) bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);           \
+        else if (op == 3) bfs_expand_exchange_kernel<S, T><<<blocks, 256, 0, st>>>(a);  \
         else bfs_traceback_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
         break;
     switch (a.n_tiles) {
@@ -351,6 +411,14 @@ int ts_bfs_expand(const ts_bfs_args* a, void* stream) {
     if (a->n_items == 0) return 0;   // an empty local frontier is normal on a multi-rank search
     if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_out_keys) return TS_E_NULL_POINTER;
     return (int)bfs_dispatch(1, *a, (cudaStream_t)stream);
+}
+
+int ts_bfs_expand_exchange(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (a->n_ranks < 1 || a->n_ranks > 64 || a->inbox_capacity < 1 || (a->parity != 0 && a->parity != 1)) return TS_E_BAD_ARGUMENT;
+    if (a->n_items == 0) return 0;
+    if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_counts || !a->d_peer_bufs) return TS_E_NULL_POINTER;
+    return (int)bfs_dispatch(3, *a, (cudaStream_t)stream);
 }
 
 int ts_bfs_traceback(const ts_bfs_args* a, void* stream) {
