@@ -96,6 +96,11 @@ SHAPES = [  # S, T, W, multi, N, K, max_steps
     (16, 8, 60, True, 2048, 64, 300),
     (16, 5, 100, False, 2048, 64, 100),
     (13, 1, 40, False, 2048, 64, 100),
+    (11, 6, 25, True, 2048, 64, 100),      # wide wall records: 9,10 -> 5 pair words, 11,12 -> 6, 13,14 -> 7, 15,16 -> 8
+    (14, 8, 50, False, 2048, 64, 100),     # widest board with edge sentinels inside the 16-bit line
+    (14, 2, 0, True, 2048, 48, 20),
+    (15, 7, 70, True, 2048, 64, 100),      # plain lines, like 16
+    (10, 8, 30, True, 2048, 64, 100),
     (5, 2, 3, True, 1021, 300, 255),       # widest 1-byte step counter; N not a multiple of 4
     (5, 2, 3, False, 1023, 300, 256),      # first 4-byte step counter
     (6, 4, 8, True, 777, 40, 1),           # every step times out
@@ -166,7 +171,8 @@ def test_ordered_goal_length_mismatch_is_rejected(ts):
 def test_observation_valid_moves_goal(ts):
     rng = np.random.default_rng(11)
     for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (4, 2, 2, True), (8, 8, 10, True),
-                           (12, 8, 36, True), (12, 8, 36, False), (16, 3, 50, False)]:
+                           (12, 8, 36, True), (12, 8, 36, False), (16, 3, 50, False), (9, 5, 20, False),
+                           (11, 2, 30, True), (14, 8, 40, False), (15, 4, 60, True)]:
         N, K = 256, 12
         blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
         actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
