@@ -183,8 +183,8 @@ def run_reference(args) -> int:
     rate, elapsed, envs_per_proc = cpu_loop_rate(cores, args.steps, args.warmup, budget_s=25.0)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": workload_config(args.gpus, ENVS_PER_GPU),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args.gpus, args.envs),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cores} processes x {envs_per_proc} envs x {args.steps} steps of the same 6x6/4-tile "
                                        "workload; oracle/py_port.py = the reference's Python step loop restated "
@@ -345,7 +345,7 @@ def run_ours(args) -> int:
         achieved = ALGO_BYTES * n_local / per_launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": workload_config(world, n_local),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": args.traffic_bytes, "kernel": f"ts::step_kernel<{S},{T}>" if S <= 8 else f"ts::wide_step_kernel<{T}>",
@@ -387,6 +387,8 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the config's)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default): the config's env count on EVERY GPU; strong: that count split over the GPUs")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
@@ -396,7 +398,8 @@ def main() -> int:
     args = ap.parse_args()
     select_config(args.config)
     if args.envs is None:
-        args.envs = ENVS_PER_GPU
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.envs = ENVS_PER_GPU if args.scaling == "weak" else -(-ENVS_PER_GPU // world)
     if args.traffic_bytes is None and args.envs == ENVS_PER_GPU:
         args.traffic_bytes = NCU_TRAFFIC_BYTES.get(args.config)
     args.warmup = max(args.warmup, 3)
