@@ -11,10 +11,6 @@ import sys
 import numpy as np
 import pytest
 
-# opt-in persistent bulk-async step kernel: exercised by the GPU parity tests (read once, at the
-# first ts_step call of the process)
-os.environ.setdefault("TS_STEP_PIPE", "1")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

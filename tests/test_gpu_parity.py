@@ -249,13 +249,14 @@ def test_synthetic_rollout_vs_oracle(ts):
 @pytest.mark.parametrize("S,T,W,multi,auto_reset,max_steps", [(6, 4, 8, True, True, 100), (6, 4, 8, False, False, 11),
                                                                (5, 1, 5, False, True, 7), (4, 2, 2, True, True, 100),
                                                                (8, 8, 12, True, True, 100), (6, 3, 4, True, False, 100)])
-def test_pipelined_kernel_matches_direct_kernel_and_oracle(ts, S, T, W, multi, auto_reset, max_steps):
-    """With TS_STEP_PIPE=1 (set for the GPU test session in conftest.py) batches of >= 2^18 envs
-    run the persistent bulk-async kernel (step_kernel_pipe); the same batch stepped through
-    65,536-env sub-ranges runs the direct kernel.  Both must agree bit
+def test_pipelined_kernel_matches_direct_kernel_and_oracle(ts, monkeypatch, S, T, W, multi, auto_reset, max_steps):
+    """With TS_STEP_PIPE=1 (the opt-in experiment, switched on for this test only) batches of
+    >= 2^18 envs run the persistent bulk-async kernel (step_kernel_pipe); the same batch stepped
+    through 65,536-env sub-ranges runs the direct kernel -- the default.  Both must agree bit
     for bit on every array, and the first 2,048 envs must match the oracle.  N is not a
     multiple of the tile, so the ragged last tile and the padding envs are exercised."""
     import ctypes as C
+    monkeypatch.setenv("TS_STEP_PIPE", "1")
     N, K = (1 << 18) + 128 * 5 + 37, 24
     kw = dict(seed=5, max_steps=max_steps, auto_reset=auto_reset, track_terminal=True)
     a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, **kw)

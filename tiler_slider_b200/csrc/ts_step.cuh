@@ -437,7 +437,8 @@ inline bool launch_step_pipe(const ts_step_args& a, cudaStream_t stream) {
 // buffers cap the pipelined kernel at fewer warps.  It needs 128-env aligned ranges and the
 // 1-byte step counter.
 inline bool use_pipe(const ts_step_args& a) {
-    static const bool enabled = [] { const char* e = getenv("TS_STEP_PIPE"); return e && e[0] == '1'; }();
+    const char* e = getenv("TS_STEP_PIPE");     // read per call: tests switch it on for one test only
+    const bool enabled = e && e[0] == '1';
     return enabled && a.count_bytes == 1 && a.first_env % CAP_ALIGN == 0 && a.n_envs >= (int64_t)1 << 18;
 }
 
