@@ -54,7 +54,7 @@ def main() -> int:
         w = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_to_all_single(torch.empty_like(w), w)
         dist.all_reduce(w)
-    BfsSolver(ts.BatchedTilerSliderEnv.synthetic(128, args.size, args.tiles, args.walls, True, seed=1, device=dev),
+    BfsSolver(ts.BatchedTilerSliderEnv.synthetic(min(128, args.puzzles), args.size, args.tiles, args.walls, True, seed=1, device=dev),
               table_capacity=1 << 22).solve(max_depth=3)      # warm the kernels / allocator
     torch.cuda.synchronize()
     if world > 1:
