@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace ts {
@@ -440,5 +441,36 @@ template <int NWORDS> __device__ __forceinline__ uint64_t board64(const uint32_t
 
 // flag bits (mirrored in include/tiler_slider.h)
 constexpr uint32_t F_DONE = 1, F_WON = 2, F_INVALID = 4, F_TIMEOUT = 8, F_STALE = 16;
+
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// The step kernels are launched with the programmatic-stream-serialization attribute: the launch
+// behind a step in the stream may place its CTAs while the step's last wave drains, which hides the
+// launch latency of back-to-back steps (measured, Python loop without a CUDA graph: 73.9 -> 71.9 us
+// per 16.7M-env step, 14.3 -> 12.6 us per 1M-env step; same as a graph replay).  The kernels execute
+// griddepcontrol.wait before their first global access, so whatever ran ahead of them in the
+// stream has completed and is visible.  TS_STEP_PDL=0 switches back to plain launches.
+__device__ __forceinline__ void dependent_launch_sync() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename K, typename A>
+inline void launch_dependent(K kernel, unsigned blocks, unsigned threads, cudaStream_t stream, const A& args) {
+    const char* e = getenv("TS_STEP_PDL");
+    if (e && e[0] == '0') {
+        kernel<<<blocks, threads, 0, stream>>>(args);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args);
+}
 
 }  // namespace ts

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     g += (uint32_t)(a.first_env / GROUP);
     const size_t cap = (size_t)a.capacity;
     const size_t e0 = (size_t)g * GROUP;
+    dependent_launch_sync();     // nothing is read before the launch ahead of us has completed (ts_common.cuh)
 
     StepInputs<S, T, GOAL, CW> in;
     // targets and step counters are only needed after the slide; under the 32-register cap the
@@ -442,6 +443,11 @@ inline bool use_pipe(const ts_step_args& a) {
     return enabled && a.count_bytes == 1 && a.first_env % CAP_ALIGN == 0 && a.n_envs >= (int64_t)1 << 18;
 }
 
+template <typename K>
+inline void launch_direct(K kernel, const ts_step_args& a, unsigned blocks, cudaStream_t stream) {
+    launch_dependent(kernel, blocks, STEP_THREADS, stream, a);
+}
+
 template <int S, int T, int GOAL>
 inline void launch_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t stream) {
     const bool ar = a.auto_reset != 0, narrow = a.count_bytes == 1;
@@ -449,10 +455,10 @@ inline void launch_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_
         const bool ok = ar ? launch_step_pipe<S, T, GOAL, true>(a, stream) : launch_step_pipe<S, T, GOAL, false>(a, stream);
         if (ok) return;
     }
-    if (ar && narrow) step_kernel<S, T, GOAL, true, 1><<<blocks, STEP_THREADS, 0, stream>>>(a);
-    else if (ar) step_kernel<S, T, GOAL, true, 4><<<blocks, STEP_THREADS, 0, stream>>>(a);
-    else if (narrow) step_kernel<S, T, GOAL, false, 1><<<blocks, STEP_THREADS, 0, stream>>>(a);
-    else step_kernel<S, T, GOAL, false, 4><<<blocks, STEP_THREADS, 0, stream>>>(a);
+    if (ar && narrow) launch_direct(step_kernel<S, T, GOAL, true, 1>, a, blocks, stream);
+    else if (ar) launch_direct(step_kernel<S, T, GOAL, true, 4>, a, blocks, stream);
+    else if (narrow) launch_direct(step_kernel<S, T, GOAL, false, 1>, a, blocks, stream);
+    else launch_direct(step_kernel<S, T, GOAL, false, 4>, a, blocks, stream);
 }
 
 template <int S, int T>

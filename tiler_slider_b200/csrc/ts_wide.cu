@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kerne
     const uint32_t i = blockIdx.x * WIDE_THREADS + threadIdx.x;
     if (i >= (uint32_t)a.n_envs) return;
     const uint32_t env = (uint32_t)a.first_env + i;
+    dependent_launch_sync();
     const uint32_t action = a.d_actions[env] & 3u;
     uint32_t q0[PR], q[PR];
     ld_pos<PW>(a.d_pos, env, q0);
@@ -337,8 +338,8 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_goal_kernel(const __grid_co
 }
 
 template <int T, int GOAL, int LW> static void launch_wide_step_lw(const ts_step_args& a, unsigned blocks, cudaStream_t st) {
-    if (a.auto_reset != 0) wide_step_kernel<T, GOAL, true, LW><<<blocks, WIDE_THREADS, 0, st>>>(a);
-    else wide_step_kernel<T, GOAL, false, LW><<<blocks, WIDE_THREADS, 0, st>>>(a);
+    if (a.auto_reset != 0) launch_dependent(wide_step_kernel<T, GOAL, true, LW>, blocks, WIDE_THREADS, st, a);
+    else launch_dependent(wide_step_kernel<T, GOAL, false, LW>, blocks, WIDE_THREADS, st, a);
 }
 template <int T, int GOAL> static void launch_wide_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t st) {
     switch (wide_line_words(a.size)) {
