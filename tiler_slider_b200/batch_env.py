@@ -271,7 +271,7 @@ class BatchedTilerSliderEnv:
 
     # ------------------------------------------------------------------ host-buffer path
     def step_host(self, h_actions: torch.Tensor, h_reward: torch.Tensor | None = None, h_done: torch.Tensor | None = None,
-                  h_flags: torch.Tensor | None = None, chunk_envs: int = 1 << 21, n_streams: int = 4) -> None:
+                  h_flags: torch.Tensor | None = None, chunk_envs: int | None = None, n_streams: int = 4) -> None:
         """The same step driven from pinned HOST buffers (ts_step_host): uploads the actions,
         runs K2 and downloads reward + done (and / or the status byte `flags`), pipelined in
         chunks; returns when everything has landed.  With only `h_flags` given, 1 byte per env
@@ -283,6 +283,8 @@ class BatchedTilerSliderEnv:
         for t, dt in ((h_actions, torch.uint8), (h_reward, torch.float32), (h_done, torch.uint8), (h_flags, torch.uint8)):
             if t is not None and (t.is_cuda or t.dtype != dt or t.numel() < self.n_envs or not t.is_contiguous()):
                 raise ValueError("step_host needs contiguous host tensors: uint8 actions, float32 reward, uint8 done / flags")
+        if chunk_envs is None:      # 2M-env chunks keep PCIe busy (profiles/r1_pcie_e2e.json); small batches: one chunk per stream
+            chunk_envs = min(1 << 21, max(1 << 16, -(-self.n_envs // n_streams)))
         if self._host_ctx is None:
             h = C.c_void_p()
             with torch.cuda.device(self.device):
