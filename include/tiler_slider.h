@@ -268,6 +268,14 @@ typedef struct ts_bfs_args {
     uint64_t *const *d_peer_bufs;
     int64_t inbox_capacity;
     int32_t parity, reserved3;
+    /* device-driven levels (ts_bfs_expand, ts_bfs_hash_insert), optional: the item count is read
+     * on the DEVICE as min(n_items, *d_n_items * n_items_scale) -- n_items is then only the
+     * bound the grid is sized for -- so consecutive levels can be launched back to back
+     * without the host learning the frontier sizes in between: expand level d with
+     * d_n_items = &new_count[d], insert with the same pointer, scale 4 and d_counts =
+     * the counter block of level d+1. */
+    const int64_t *d_n_items;
+    int64_t n_items_scale;
 } ts_bfs_args;
 #define TS_BFS_XHDR 16
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
@@ -280,6 +288,16 @@ int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
  * of the sent counts doubles as the termination test) and alternates `parity` level by level. */
 int ts_bfs_expand_exchange(const ts_bfs_args *a, void *stream);
 int ts_bfs_traceback(const ts_bfs_args *a, void *stream);
+/* n_levels device-driven BFS levels launched back to back (2 kernels per level, no host sync):
+ * level d = first_depth .. first_depth + n_levels - 1 expands the lvl[4*d] keys of
+ * front[d & 1] into succ (4 * frontier_capacity keys) and inserts them as level d+1 into
+ * front[(d+1) & 1], counters in lvl[4*(d+1) ..] = (new keys, goal successors, overflow, -),
+ * which must be zero on entry.  `a` supplies the puzzle tables, d_table / table_capacity, the
+ * optional parent table (d_table_parent; parents are the frontier keys) and per-puzzle tallies.
+ * known_frontier >= 0: the host knows the size of level first_depth (n_levels must be 1): that
+ * level is launched with a grid of its own size instead of one persistent wave. */
+int ts_bfs_levels(const ts_bfs_args *a, int32_t first_depth, int32_t n_levels, uint64_t *front0, uint64_t *front1,
+                  uint64_t *succ, int64_t *lvl, int64_t frontier_capacity, int64_t known_frontier, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * ts_step_host: the same step through HOST buffers (the call a host-side driver makes):

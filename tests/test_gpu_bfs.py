@@ -118,6 +118,26 @@ def test_more_than_four_tiles_single_puzzle(ts):
     assert (res.n_states, res.levels, res.solve_depth) == (ns, lv, depth)
 
 
+def test_device_driven_and_host_driven_searches_agree(ts):
+    """The single-rank default keeps the frontier sizes on the device and launches 16 levels
+    between host read-backs; the host-driven loop (one read-back per level, the multi-rank
+    code path) must give the same search: level histogram, per-puzzle tallies, solution lengths."""
+    from tiler_slider_b200.bfs import BfsSolver
+    table = ts.BatchedTilerSliderEnv.synthetic(512, 6, 4, 8, True, seed=77)
+    for kw in (dict(), dict(with_paths=True), dict(max_depth=5), dict(max_depth=16), dict(max_depth=17)):
+        a = BfsSolver(table, table_capacity=1 << 22).solve(device_driven=True, **kw)
+        b = BfsSolver(table, table_capacity=1 << 22).solve(device_driven=False, **kw)
+        assert (a.n_states, a.levels, a.solve_depth, a.generated) == (b.n_states, b.levels, b.solve_depth, b.generated), kw
+        assert torch.equal(a.states_per_puzzle, b.states_per_puzzle)
+        assert torch.equal(a.solve_depth_per_puzzle, b.solve_depth_per_puzzle)
+        if kw.get("with_paths"):
+            assert [None if x is None else len(x) for x in a.solutions] == [None if x is None else len(x) for x in b.solutions]
+    single = ts.BatchedTilerSliderEnv.synthetic(1, 6, 4, 8, False, seed=3)
+    a = BfsSolver(single, table_capacity=1 << 18).solve(device_driven=True)
+    b = BfsSolver(single, table_capacity=1 << 18).solve(device_driven=False)
+    assert (a.n_states, a.levels, a.solve_depth, a.generated) == (b.n_states, b.levels, b.solve_depth, b.generated)
+
+
 def test_table_overflow_is_reported(ts, golden_misc):
     from tiler_slider_b200.bfs import solve_puzzle
     b = [x for x in golden_misc["bfs"] if x["name"] == "puzzle_multi_180"][0]

@@ -77,7 +77,8 @@ class BfsArgs(C.Structure):
                 ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64),
                 ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_goal_keys", _vp),
                 ("depth", _i32), ("reserved2", _i32),
-                ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("reserved3", _i32)]
+                ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("reserved3", _i32),
+                ("d_n_items", _vp), ("n_items_scale", _i64)]
 
 
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
@@ -103,6 +104,7 @@ SYMBOLS = {
     "ts_bfs_seed": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_expand": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_expand_exchange": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_levels": (C.c_int, [C.POINTER(BfsArgs), C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "ts_bfs_partition_count": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),

@@ -131,6 +131,24 @@ class CudaBfsKernels:
     def new_table(self, capacity: int) -> torch.Tensor:
         return torch.full((capacity,), NONE, dtype=torch.int64, device=self.device)
 
+    # ---- device-driven levels: frontier sizes stay on the device ------------------------------
+    def levels_on_device(self, table: torch.Tensor, front: list, succ: torch.Tensor, lvl: torch.Tensor,
+                         first_depth: int, n_levels: int, parent_table: torch.Tensor | None,
+                         stats: "BfsStats | None", known_frontier: int = -1) -> None:
+        """ts_bfs_levels: expand level d and insert its successors as level d+1, for n_levels
+        consecutive levels, without the host knowing any frontier size: lvl is int64[levels, 4] =
+        (new keys, goal successors, overflow, -) per level; front[d & 1] holds lvl[d, 0] keys."""
+        kw = {}
+        if stats is not None:
+            kw = dict(d_states_per_puzzle=stats.states.data_ptr(), d_solve_depth=stats.solve_depth.data_ptr(),
+                      d_goal_keys=None if stats.goal_keys is None else stats.goal_keys.data_ptr())
+        a = self._args(table_capacity=table.numel(), d_table=table.data_ptr(),
+                       d_table_parent=None if parent_table is None else parent_table.data_ptr(), **kw)
+        with torch.cuda.device(self.device):
+            check(self.lib.ts_bfs_levels(C.byref(a), first_depth, n_levels, front[0].data_ptr(), front[1].data_ptr(),
+                                         succ.data_ptr(), lvl.data_ptr(), front[0].numel(), known_frontier,
+                                         torch.cuda.current_stream(self.device).cuda_stream), "ts_bfs_levels")
+
     # ---- exchange through NVLink peer memory (ts_bfs_expand_exchange) ----------------------
     XHDR = 16                                   # TS_BFS_XHDR: header words ahead of the two inboxes
 
@@ -299,12 +317,85 @@ class BfsSolver:
         k._xbuf[parity: parity + 1].zero_()        # nobody writes this inbox again before the level after next
         return k.inbox(parity, n_in), bool(n_sent)
 
-    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
+    LEVELS_PER_SYNC = 16        # device-driven search: levels launched between two host read-backs
+    BIG_LEVEL = 1 << 19         # frontiers from this size on get their own launch geometry and read-back
+
+    def _solve_on_device(self, max_depth: int, per_puzzle: bool, with_paths: bool) -> BfsResult:
+        """Single rank: the frontier sizes never leave the device.  The kernels read their item
+        counts from the per-level counter blocks the previous insert filled, so LEVELS_PER_SYNC
+        levels are launched back to back and the host only looks every so often whether the
+        frontier has run dry (levels launched past that point find a zero count and do nothing).
+        A host-driven level costs a round trip of 0.1-0.2 ms, and most levels of a search are
+        far smaller than that."""
+        k, P, dev = self.k, self.n_puzzles, self.k.device
+        table = k.new_table(self.table_capacity)
+        parent_table = k.new_table(self.table_capacity) if with_paths else None
+        goal_keys = torch.full((P,), NONE, dtype=torch.int64, device=dev) if with_paths else None
+        states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
+        depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
+        stats = BfsStats(states_pp, depth_pp, goal_keys) if per_puzzle else None
+        cap = max(1 << 16, P, min(self.table_capacity // 4, 1 << 28))          # frontier capacity
+        front = [k.workspace("front0", cap), k.workspace("front1", cap)]
+        succ = k.workspace("succ", 4 * cap)
+        n_lvl = 256
+        lvl = torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)
+        # depth 0 through the ordinary insert (host knows P); its new keys land in the workspace
+        # buffer out{flip}: copy them to front0 and seed the counters
+        seeds, _ = k.insert(table, k.seed(), None, parent_table, stats) if stats is not None else \
+            k.insert(table, k.seed(), None, parent_table)
+        front[0][: seeds.numel()].copy_(seeds)
+        lvl[0, 0] = seeds.numel()
+        depth, rows, known = 0, None, seeds.numel()
+        while depth < max_depth:
+            # a big level is worth a grid of its own size and a read-back of its own; small ones are
+            # launched LEVELS_PER_SYNC at a time as single persistent waves that find their size on the device
+            big = known >= self.BIG_LEVEL
+            batch = 1 if big else min(self.LEVELS_PER_SYNC, max_depth - depth)
+            if depth + batch + 1 > n_lvl:                                     # more counter blocks
+                lvl = torch.cat([lvl, torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)])
+                n_lvl *= 2
+            k.levels_on_device(table, front, succ, lvl, depth, batch, parent_table, stats, known if big else -1)
+            depth += batch
+            rows = lvl[: depth + 1].tolist()                                  # the only host sync of the batch
+            if any(r[2] for r in rows):
+                raise RuntimeError("BFS visited table is full (or a frontier outgrew its buffer): raise table_capacity")
+            if any(r[0] == 0 for r in rows):
+                break
+            known = rows[-1][0]
+        rows = rows if rows is not None else lvl[:1].tolist()
+        levels = [r[0] for r in rows]
+        won_per_level = [r[1] for r in rows]
+        if 0 in levels:
+            cut = levels.index(0)
+            levels, won_per_level = levels[:cut], won_per_level[: cut + 1]
+        generated = 4 * sum(levels[:max_depth] if len(levels) > max_depth else levels)
+        solve_depth = next((d for d, w in enumerate(won_per_level) if w), -1)
+        if per_puzzle:
+            depth_pp = torch.where(depth_pp >= (1 << 30), torch.full_like(depth_pp, -1), depth_pp)
+        solutions = None
+        if with_paths:
+            max_moves = max(1, int(depth_pp.max()))
+            moves, lengths = k.traceback(table, parent_table, goal_keys, max_moves)
+            mv, ln = moves.cpu().tolist(), lengths.cpu().tolist()
+            solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
+        return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
+                         solve_depth_per_puzzle=depth_pp, generated=generated, solutions=solutions)
+
+    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False,
+              device_driven: bool | None = None) -> BfsResult:
         """Search every puzzle to exhaustion (or max_depth).  with_paths (single rank only): also
-        record parents and return a shortest solution string per puzzle."""
+        record parents and return a shortest solution string per puzzle.
+        device_driven (default: on for a single rank on the CUDA kernels): see _solve_on_device."""
         k, P = self.k, self.n_puzzles
         if with_paths and (self.world > 1 or not per_puzzle):
             raise ValueError("with_paths needs a single-rank search with per_puzzle statistics")
+        can = self.world == 1 and isinstance(k, CudaBfsKernels) and not self.profile
+        if device_driven is None:
+            device_driven = can
+        if device_driven:
+            if not can:
+                raise ValueError("device-driven search needs a single rank on the CUDA kernels (and no phase profiling)")
+            return self._solve_on_device(max_depth, per_puzzle, with_paths)
         table = k.new_table(self.table_capacity)
         parent_table = k.new_table(self.table_capacity) if with_paths else None
         dev = k.device

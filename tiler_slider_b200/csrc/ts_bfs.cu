@@ -23,6 +23,7 @@
 namespace ts {
 
 constexpr uint64_t BFS_NONE = ~0ull;
+constexpr unsigned BFS_PERSISTENT_BLOCKS = 148 * 8;   // one wave of 256-thread CTAs on a B200
 constexpr uint64_t BFS_WON_BIT = 1ull << 63;
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
@@ -108,15 +109,25 @@ __device__ __forceinline__ void successors(const ts_bfs_args& a, uint64_t in_key
     }
 }
 
-// K4: thread = one frontier state, four successors
+// number of items of a launch: the host's n_items, or (device-driven levels) what an earlier
+// kernel left in *d_n_items
+__device__ __forceinline__ int64_t item_count(const ts_bfs_args& a) {
+    if (!a.d_n_items) return a.n_items;
+    const int64_t n = *a.d_n_items * a.n_items_scale;
+    return n < a.n_items ? n : a.n_items;
+}
+
+// K4: thread = one frontier state, four successors (grid-stride: the grid may be smaller than
+// the frontier when its size is only known on the device)
 template <int S, int T>
 __global__ void __launch_bounds__(256) bfs_expand_kernel(const ts_bfs_args a) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.n_items) return;
-    uint64_t key[4];
-    successors<S, T>(a, a.d_in_keys[i], key);
+    const int64_t n = item_count(a);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        uint64_t key[4];
+        successors<S, T>(a, a.d_in_keys[i], key);
 #pragma unroll
-    for (int d = 0; d < 4; ++d) a.d_out_keys[4 * i + d] = key[d];
+        for (int d = 0; d < 4; ++d) a.d_out_keys[4 * i + d] = key[d];
+    }
 }
 
 // owner rank of a key (won bit excluded)
@@ -227,9 +238,12 @@ __global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_a
 // appended to d_out_keys through the cursor d_counts[0]; d_counts[1] counts won successors seen,
 // d_counts[2] is set when the table is full.
 __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args a) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n_items = item_count(a);
     const unsigned lane = threadIdx.x & 31u;
-    const uint64_t raw = i < a.n_items ? a.d_in_keys[i] : BFS_NONE;
+    // grid-stride over whole blocks of 256 items, so every warp runs the same number of rounds
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n_items; base += (int64_t)gridDim.x * 256) {
+    const int64_t i = base + threadIdx.x;
+    const uint64_t raw = i < n_items ? a.d_in_keys[i] : BFS_NONE;
     const bool live = raw != BFS_NONE;
     const uint64_t key = raw & ~BFS_WON_BIT;
     bool is_new = false, full = false;
@@ -293,6 +307,7 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
         }
     }
     if (full) a.d_counts[2] = 1;
+    }
 }
 
 // slot of `key` in the visited table, or -1
@@ -350,7 +365,8 @@ __global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a)
 }
 
 template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((a.n_items + 255) / 256);
+    unsigned blocks = (unsigned)((a.n_items + 255) / 256);
+    if (a.d_n_items && blocks > BFS_PERSISTENT_BLOCKS) blocks = BFS_PERSISTENT_BLOCKS;   // size unknown on the host: grid-stride
 #define TS_BFS_CASE(T)                                                                  \
     case T:                                                                             \
         if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
@@ -421,6 +437,40 @@ int ts_bfs_expand_exchange(const ts_bfs_args* a, void* stream) {
     return (int)bfs_dispatch(3, *a, (cudaStream_t)stream);
 }
 
+int ts_bfs_levels(const ts_bfs_args* a, int32_t first_depth, int32_t n_levels, uint64_t* front0, uint64_t* front1,
+                  uint64_t* succ, int64_t* lvl, int64_t frontier_capacity, int64_t known_frontier, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (!front0 || !front1 || !succ || !lvl || !a->d_table || !a->d_walls || !a->d_targets_packed) return TS_E_NULL_POINTER;
+    if (first_depth < 0 || n_levels < 0 || frontier_capacity < 1) return TS_E_BAD_ARGUMENT;
+    if (known_frontier >= 0 && (n_levels != 1 || known_frontier > frontier_capacity)) return TS_E_BAD_ARGUMENT;
+    const bool exact = known_frontier >= 0;
+    if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
+    for (int32_t d = first_depth; d < first_depth + n_levels; ++d) {
+        uint64_t* in = (d & 1) ? front1 : front0;
+        uint64_t* out = (d & 1) ? front0 : front1;
+        ts_bfs_args e = *a;                       // K4: frontier -> 4 successors each
+        e.n_items = exact ? known_frontier : frontier_capacity;
+        e.d_n_items = exact ? nullptr : lvl + 4 * (int64_t)d;
+        e.n_items_scale = 1;
+        e.d_in_keys = in;
+        e.d_out_keys = succ;
+        if (int rc = ts_bfs_expand(&e, stream)) return rc;
+        ts_bfs_args k = *a;                       // K5: successors -> table, new keys = next frontier
+        k.n_items = 4 * (exact ? known_frontier : frontier_capacity);
+        k.d_n_items = exact ? nullptr : lvl + 4 * (int64_t)d;
+        k.n_items_scale = 4;
+        k.d_in_keys = succ;
+        k.d_out_keys = out;
+        k.out_capacity = frontier_capacity;
+        k.d_counts = reinterpret_cast<uint64_t*>(lvl + 4 * (int64_t)(d + 1));
+        k.d_parent_keys = a->d_table_parent ? in : nullptr;
+        k.depth = d + 1;
+        k.d_won_keys = nullptr;
+        if (int rc = ts_bfs_hash_insert(&k, stream)) return rc;
+    }
+    return 0;
+}
+
 int ts_bfs_traceback(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, true)) return rc;
     if (a->n_items == 0) return 0;
@@ -452,7 +502,9 @@ int ts_bfs_hash_insert(const ts_bfs_args* a, void* stream) {
     if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
     if (!a->d_in_keys || !a->d_counts || !a->d_out_keys || !a->d_table) return TS_E_NULL_POINTER;
-    bfs_hash_insert_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    unsigned blocks = (unsigned)((a->n_items + 255) / 256);
+    if (a->d_n_items && blocks > BFS_PERSISTENT_BLOCKS) blocks = BFS_PERSISTENT_BLOCKS;
+    bfs_hash_insert_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
