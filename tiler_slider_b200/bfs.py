@@ -182,6 +182,28 @@ class CudaBfsKernels:
                        inbox_capacity=self._xcap, parity=parity)
         self._call(self.lib.ts_bfs_expand_exchange, a, "ts_bfs_expand_exchange")
 
+    def expand_exchange_on_device(self, front: torch.Tensor, n_ptr: int, parity: int, xcounts: torch.Tensor) -> None:
+        """K4x on a frontier whose size sits in device memory (*n_ptr); xcounts = int64[4] of this
+        level: [2] overflow, [3] keys sent."""
+        a = self._args(n_items=front.numel(), n_ranks=self._xworld, d_in_keys=front.data_ptr(),
+                       d_counts=xcounts.data_ptr(), d_peer_bufs=self._xpeers.data_ptr(),
+                       inbox_capacity=self._xcap, parity=parity, d_n_items=n_ptr, n_items_scale=1)
+        self._call(self.lib.ts_bfs_expand_exchange, a, "ts_bfs_expand_exchange")
+
+    def insert_inbox_on_device(self, table: torch.Tensor, parity: int, out: torch.Tensor, counts: torch.Tensor,
+                               stats: "BfsStats | None", depth: int) -> None:
+        """K5 over what arrived in inbox `parity` (its arrival cursor is the item count, read on
+        the device); new keys -> out, counters -> counts = int64[4] of the new level."""
+        kw = {}
+        if stats is not None:
+            kw = dict(d_states_per_puzzle=stats.states.data_ptr(), d_solve_depth=stats.solve_depth.data_ptr(),
+                      d_goal_keys=None, depth=depth)
+        o = self.XHDR + parity * self._xcap
+        a = self._args(n_items=self._xcap, table_capacity=table.numel(), out_capacity=out.numel(),
+                       d_in_keys=self._xbuf[o:].data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
+                       d_counts=counts.data_ptr(), d_n_items=self._xbuf[parity:].data_ptr(), n_items_scale=1, **kw)
+        self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
+
     def inbox(self, parity: int, n: int) -> torch.Tensor:
         o = self.XHDR + parity * self._xcap
         return self._xbuf[o: o + n]
@@ -317,6 +339,63 @@ class BfsSolver:
         k._xbuf[parity: parity + 1].zero_()        # nobody writes this inbox again before the level after next
         return k.inbox(parity, n_in), bool(n_sent)
 
+    def _solve_p2p_on_device(self, max_depth: int, per_puzzle: bool) -> BfsResult:
+        """Several ranks, peer-memory exchange, frontier sizes on the device.  Per level and rank:
+        K4x (frontier -> the owners' inboxes), an all-reduce of the sent counts (orders the ranks,
+        and its result is what the termination test reads later), K5 over the own inbox (item
+        count = its arrival cursor, read on the device), cursor reset -- LEVELS_PER_SYNC levels in
+        a row without a host read-back.  Every rank takes the same decisions because it decides
+        on all-reduced numbers only."""
+        k, P, dev = self.k, self.n_puzzles, self.k.device
+        table = k.new_table(self.table_capacity)
+        states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
+        depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
+        stats = BfsStats(states_pp, depth_pp, None) if per_puzzle else None
+        cap = max(1 << 16, P, min(self.table_capacity // 4, 1 << 28))
+        front = [k.workspace("front0", cap), k.workspace("front1", cap)]
+        n_lvl = 256
+        lvl = torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)       # per level: new keys, goal successors, overflow, -
+        xlvl = torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)      # per level: -, -, inbox overflow, keys sent (all-reduced)
+        # depth 0: seeds to their owners through the NCCL path, ordinary insert
+        mine, _ = self._exchange(k.seed())
+        seeds, _ = k.insert(table, mine, None, None, stats) if stats is not None else k.insert(table, mine)
+        front[0][: seeds.numel()].copy_(seeds)
+        lvl[0, 0] = seeds.numel()
+        depth, rows, xrows = 0, None, None
+        while depth < max_depth:
+            batch = min(self.LEVELS_PER_SYNC, max_depth - depth)
+            if depth + batch + 1 > n_lvl:
+                lvl = torch.cat([lvl, torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)])
+                xlvl = torch.cat([xlvl, torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)])
+                n_lvl *= 2
+            for d in range(depth, depth + batch):
+                parity = d & 1
+                k.expand_exchange_on_device(front[parity], lvl[d].data_ptr(), parity, xlvl[d])
+                dist.all_reduce(xlvl[d, 3:4], group=self.group)
+                k.insert_inbox_on_device(table, parity, front[parity ^ 1], lvl[d + 1], stats, d + 1)
+                k._xbuf[parity: parity + 1].zero_()    # nobody writes this inbox again before the level after next
+            depth += batch
+            both = torch.cat([lvl[: depth + 1], xlvl[: depth + 1]], dim=1).tolist()      # the host sync of the batch
+            rows, xrows = [r[:4] for r in both], [r[4:] for r in both]
+            if any(r[2] for r in rows) or any(x[2] for x in xrows) or int(k._xbuf[2].item()):
+                raise RuntimeError("BFS visited table is full (or an inbox / frontier outgrew its buffer): raise table_capacity")
+            if any(x[3] == 0 for x in xrows[:depth]):      # a level in which no rank sent anything: the search is over
+                break
+        # tallies over all ranks; counter rows past the end of the search are zero
+        tally = lvl[: depth + 1, :2].t().contiguous()       # [new keys per level, goal successors per level]
+        dist.all_reduce(tally, group=self.group)
+        levels, won_per_level = tally[0].tolist(), tally[1].tolist()
+        while len(levels) > 1 and levels[-1] == 0:
+            levels.pop()
+        generated = 4 * sum(levels[:max_depth] if len(levels) > max_depth else levels)   # 4 per key of every expanded level
+        solve_depth = next((d for d, w in enumerate(won_per_level) if w), -1)
+        if per_puzzle:
+            dist.all_reduce(states_pp, group=self.group)
+            dist.all_reduce(depth_pp, op=dist.ReduceOp.MIN, group=self.group)
+            depth_pp = torch.where(depth_pp >= (1 << 30), torch.full_like(depth_pp, -1), depth_pp)
+        return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
+                         solve_depth_per_puzzle=depth_pp, generated=generated)
+
     LEVELS_PER_SYNC = 16        # device-driven search: levels launched between two host read-backs
     BIG_LEVEL = 1 << 19         # frontiers from this size on get their own launch geometry and read-back
 
@@ -390,11 +469,15 @@ class BfsSolver:
         if with_paths and (self.world > 1 or not per_puzzle):
             raise ValueError("with_paths needs a single-rank search with per_puzzle statistics")
         can = self.world == 1 and isinstance(k, CudaBfsKernels) and not self.profile
+        can_p2p = self.world > 1 and self.exchange == "p2p" and not self.profile and not with_paths
         if device_driven is None:
-            device_driven = can
+            device_driven = can or can_p2p
         if device_driven:
+            if can_p2p:
+                return self._solve_p2p_on_device(max_depth, per_puzzle)
             if not can:
-                raise ValueError("device-driven search needs a single rank on the CUDA kernels (and no phase profiling)")
+                raise ValueError("device-driven search needs the CUDA kernels on one rank, or the peer-memory "
+                                 "exchange on several (and no phase profiling)")
             return self._solve_on_device(max_depth, per_puzzle, with_paths)
         table = k.new_table(self.table_capacity)
         parent_table = k.new_table(self.table_capacity) if with_paths else None

@@ -194,42 +194,48 @@ template <int S, int T>
 __global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_args a) {
     __shared__ unsigned int hist[64];
     __shared__ unsigned long long base[64];
-    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    uint64_t key[4] = {BFS_NONE, BFS_NONE, BFS_NONE, BFS_NONE};
-    if (i < a.n_items) successors<S, T>(a, a.d_in_keys[i], key);
-    uint32_t owner[4], slot[4];
+    const int64_t n_items = item_count(a);
+    // grid-stride over whole blocks of 256 frontier keys (the frontier size may only be known on
+    // the device, ts_bfs_args.d_n_items); every thread of a block runs the same rounds
+    for (int64_t first = (int64_t)blockIdx.x * 256; first < n_items; first += (int64_t)gridDim.x * 256) {
+        if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t i = first + threadIdx.x;
+        uint64_t key[4] = {BFS_NONE, BFS_NONE, BFS_NONE, BFS_NONE};
+        if (i < n_items) successors<S, T>(a, a.d_in_keys[i], key);
+        uint32_t owner[4], slot[4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        const bool live = key[d] != BFS_NONE;
-        owner[d] = live ? key_owner(key[d], (uint32_t)a.n_ranks) : 0u;
-        slot[d] = block_bucket_slot(hist, live, owner[d]);
-    }
-    __syncthreads();
-    if (threadIdx.x < a.n_ranks) {
-        const unsigned n = hist[threadIdx.x];
-        unsigned long long b = ~0ull;
-        if (n) {
-            uint64_t* peer = a.d_peer_bufs[threadIdx.x];
-            b = atomicAdd_system((unsigned long long*)(peer + a.parity), (unsigned long long)n);
-            if (b + n > (unsigned long long)a.inbox_capacity) {      // inbox full: drop and report
-                peer[2] = 1;
-                a.d_counts[2] = 1;
-                b = ~0ull;
-            }
-            atomicAdd((unsigned long long*)&a.d_counts[3], (unsigned long long)n);
+        for (int d = 0; d < 4; ++d) {
+            const bool live = key[d] != BFS_NONE;
+            owner[d] = live ? key_owner(key[d], (uint32_t)a.n_ranks) : 0u;
+            slot[d] = block_bucket_slot(hist, live, owner[d]);
         }
-        base[threadIdx.x] = b;
-    }
-    __syncthreads();
+        __syncthreads();
+        if (threadIdx.x < a.n_ranks) {
+            const unsigned n = hist[threadIdx.x];
+            unsigned long long b = ~0ull;
+            if (n) {
+                uint64_t* peer = a.d_peer_bufs[threadIdx.x];
+                b = atomicAdd_system((unsigned long long*)(peer + a.parity), (unsigned long long)n);
+                if (b + n > (unsigned long long)a.inbox_capacity) {      // inbox full: drop and report
+                    peer[2] = 1;
+                    a.d_counts[2] = 1;
+                    b = ~0ull;
+                }
+                atomicAdd((unsigned long long*)&a.d_counts[3], (unsigned long long)n);
+            }
+            base[threadIdx.x] = b;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        if (key[d] == BFS_NONE) continue;
-        const unsigned long long b = base[owner[d]];
-        if (b == ~0ull) continue;
-        uint64_t* inbox = a.d_peer_bufs[owner[d]] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
-        inbox[b + slot[d]] = key[d];
+        for (int d = 0; d < 4; ++d) {
+            if (key[d] == BFS_NONE) continue;
+            const unsigned long long b = base[owner[d]];
+            if (b == ~0ull) continue;
+            uint64_t* inbox = a.d_peer_bufs[owner[d]] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
+            inbox[b + slot[d]] = key[d];
+        }
+        __syncthreads();                                                  // base[] is reused by the next round
     }
     __threadfence_system();
 }
