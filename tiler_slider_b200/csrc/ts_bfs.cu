@@ -190,25 +190,36 @@ __global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs
 // arrival cursor, and stores the keys straight into the owners' inboxes -- for a remote owner
 // these are posted writes through the NVLink mapping.  No partition pass over the successors, no
 // size exchange, no all-to-all; nothing here waits on another GPU.
+constexpr int XCHG_STATES = 4;     // frontier states per thread and round of K4x
+
 template <int S, int T>
 __global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_args a) {
     __shared__ unsigned int hist[64];
     __shared__ unsigned long long base[64];
     const int64_t n_items = item_count(a);
-    // grid-stride over whole blocks of 256 frontier keys (the frontier size may only be known on
-    // the device, ts_bfs_args.d_n_items); every thread of a block runs the same rounds
-    for (int64_t first = (int64_t)blockIdx.x * 256; first < n_items; first += (int64_t)gridDim.x * 256) {
+    constexpr int64_t ROUND = 256 * XCHG_STATES;
+    // grid-stride over rounds of 1,024 frontier keys = 4,096 successors per block (the frontier size
+    // may only be known on the device, ts_bfs_args.d_n_items).  One reservation per owner and round:
+    // the arrival cursors are single addresses that every block of every rank adds to, so the fewer
+    // and larger the reservations the better (at 256 keys per round an 8-GPU search spent more time
+    // queueing on them than inserting).
+    for (int64_t first = (int64_t)blockIdx.x * ROUND; first < n_items; first += (int64_t)gridDim.x * ROUND) {
         if (threadIdx.x < 64) hist[threadIdx.x] = 0;
         __syncthreads();
-        const int64_t i = first + threadIdx.x;
-        uint64_t key[4] = {BFS_NONE, BFS_NONE, BFS_NONE, BFS_NONE};
-        if (i < n_items) successors<S, T>(a, a.d_in_keys[i], key);
-        uint32_t owner[4], slot[4];
+        uint64_t key[XCHG_STATES][4];
+        uint32_t where[XCHG_STATES][4];                    // owner | slot << 8
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const bool live = key[d] != BFS_NONE;
-            owner[d] = live ? key_owner(key[d], (uint32_t)a.n_ranks) : 0u;
-            slot[d] = block_bucket_slot(hist, live, owner[d]);
+        for (int s = 0; s < XCHG_STATES; ++s) {
+            const int64_t i = first + s * 256 + threadIdx.x;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) key[s][d] = BFS_NONE;
+            if (i < n_items) successors<S, T>(a, a.d_in_keys[i], key[s]);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const bool live = key[s][d] != BFS_NONE;
+                const uint32_t owner = live ? key_owner(key[s][d], (uint32_t)a.n_ranks) : 0u;
+                where[s][d] = owner | (block_bucket_slot(hist, live, owner) << 8);
+            }
         }
         __syncthreads();
         if (threadIdx.x < a.n_ranks) {
@@ -228,14 +239,17 @@ __global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_a
         }
         __syncthreads();
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            if (key[d] == BFS_NONE) continue;
-            const unsigned long long b = base[owner[d]];
-            if (b == ~0ull) continue;
-            uint64_t* inbox = a.d_peer_bufs[owner[d]] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
-            inbox[b + slot[d]] = key[d];
-        }
-        __syncthreads();                                                  // base[] is reused by the next round
+        for (int s = 0; s < XCHG_STATES; ++s)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (key[s][d] == BFS_NONE) continue;
+                const uint32_t owner = where[s][d] & 0xFFu;
+                const unsigned long long b = base[owner];
+                if (b == ~0ull) continue;
+                uint64_t* inbox = a.d_peer_bufs[owner] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
+                inbox[b + (where[s][d] >> 8)] = key[s][d];
+            }
+        __syncthreads();                                                  // hist / base are reused by the next round
     }
     __threadfence_system();
 }
@@ -372,6 +386,7 @@ __global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a)
 
 template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a, cudaStream_t st) {
     unsigned blocks = (unsigned)((a.n_items + 255) / 256);
+    if (op == 3) blocks = (unsigned)((a.n_items + 256 * XCHG_STATES - 1) / (256 * XCHG_STATES));
     if (a.d_n_items && blocks > BFS_PERSISTENT_BLOCKS) blocks = BFS_PERSISTENT_BLOCKS;   // size unknown on the host: grid-stride
 #define TS_BFS_CASE(T)                                                                  \
     case T:                                                                             \
