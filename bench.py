@@ -43,7 +43,7 @@ METRIC = "env-steps/sec at 1/2/4/8 B200 and % HBM roofline vs reference CPU step
 UNIT = "env-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default
 # size, from the committed `ncu --set full` capture (profiles/r1_final_step_kernel_full_raw.csv)
-NCU_TRAFFIC_BYTES = {"c3": 268.497152e6 + 128.130560e6}
+NCU_TRAFFIC_BYTES = {"c3": 268.448512e6 + 126.243840e6}
 N_ACTION_ROWS = 8                               # distinct pre-generated action vectors, cycled
 
 
