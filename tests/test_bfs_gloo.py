@@ -117,6 +117,26 @@ def test_bfs_driver_over_gloo(world):
     assert generated == 4 * n_states
 
 
+def test_bfs_driver_argument_checks():
+    """Exchange / device-driven options that need the CUDA kernels are refused, not ignored, when
+    the driver runs on stand-in kernels."""
+    sys.path.insert(0, ROOT)
+    from tiler_slider_b200.bfs import BfsSolver
+    gold = {b["name"]: b for b in _golden_bfs()}
+    kernels = OracleBfsKernels([gold["puzzle_multi_111"]])
+    with pytest.raises(ValueError, match="exchange"):
+        BfsSolver(kernels=kernels, n_puzzles=1, exchange="carrier pigeon")
+    with pytest.raises(ValueError, match="power of two"):
+        BfsSolver(kernels=kernels, n_puzzles=1, table_capacity=1000)
+    solver = BfsSolver(kernels=kernels, n_puzzles=1, table_capacity=1 << 12, exchange="p2p")   # one rank: nothing to exchange
+    assert solver.exchange == "nccl"
+    with pytest.raises(ValueError, match="device-driven"):
+        solver.solve(device_driven=True)
+    with pytest.raises(ValueError, match="with_paths"):
+        solver.solve(with_paths=True, per_puzzle=False)
+    assert solver.solve(max_depth=2).levels == gold["puzzle_multi_111"]["levels"][:3]
+
+
 def test_shard_and_reduce_over_gloo():
     """The step path's only multi-rank logic: disjoint contiguous shards + a MAX reduce of the
     per-rank time, as bench.py does it."""
