@@ -147,3 +147,32 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.lower(), fn
     assert "oracle" not in open(os.path.join(ROOT, "main.py")).read().lower()
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """Every POD argument struct of include/tiler_slider.h, compiled as plain C by gcc, has the
+    size and the field offsets of its ctypes mirror in _lib.py (the header is the ABI; the
+    mirrors are what the Python host passes)."""
+    import ctypes as C
+    import subprocess
+    from tiler_slider_b200 import _lib
+    pairs = {"ts_encode_args": _lib.EncodeArgs, "ts_synth_args": _lib.SynthArgs, "ts_step_args": _lib.StepArgs,
+             "ts_observe_args": _lib.ObserveArgs, "ts_valid_args": _lib.ValidArgs, "ts_goal_args": _lib.GoalArgs,
+             "ts_bfs_args": _lib.BfsArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tiler_slider.h"', 'int main(void) {']
+    for cname, mirror in pairs.items():
+        lines.append(f'printf("SIZEOF {cname} - %zu\\n", sizeof({cname}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'printf("OFFSET {cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ['return 0;', '}']
+    src, exe = tmp_path / "abi.c", tmp_path / "abi"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert len(out) > 100
+    for line in out:
+        kind, cname, field, value = line.split()
+        if kind == "SIZEOF":
+            assert int(value) == C.sizeof(pairs[cname]), f"sizeof({cname})"
+        else:
+            assert int(value) == getattr(pairs[cname], field).offset, f"{cname}.{field}"
