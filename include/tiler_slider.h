@@ -23,8 +23,11 @@
  * Packed layout (struct-of-arrays, environment index innermost):
  *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.  EVERY per-env
  *    array handed to the library (state, actions, reward, done, flags, ...) must hold
- *    `capacity` elements: kernels work on whole 4-env groups / 128-env tiles and may read and
- *    write the padding environments between n_envs and capacity (their content is unspecified).
+ *    `capacity` elements.  ts_step reads and writes exactly the envs of its range
+ *    [first_env, first_env + n_envs): whole 4-env groups go through the vectorised kernel, the
+ *    ragged end (n_envs % 4 envs) through a per-env kernel.  The pure queries ts_valid_moves and
+ *    ts_goal_check may also WRITE their (correct) result for the up-to-3 envs that share the last
+ *    4-env group of the range.
  *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = row*PS + col of tile
  *    i (PS = ts_pos_stride(S)), unused bytes zero.  Arrays: pos (in/out), init, targets
  *    (ordered mode).
@@ -40,8 +43,9 @@
  *    c, one bit per row), used by UP/DOWN; ts_walls_bytes(S) = 4*L bytes per env, of which a
  *    step reads the 2*L bytes of one axis.  S <= 14: cell k of a
  *    line is bit k+1, and bit 0 and bit S+1 of every line are set (edge sentinels); S = 15, 16:
- *    cell k is bit k, no sentinel.  Set-goal target board = u16 [capacity][16 rows], cell
- *    (r,c) = bit c of line r.  PS = 16.
+ *    cell k is bit k, no sentinel.  Set-goal target record = u16 [capacity][17]: 16 rows, cell
+ *    (r,c) = bit c of word r, then the number of distinct target cells (the step kernels test
+ *    "every tile on a target cell" plus "that number == n_tiles", which is set equality).  PS = 16.
  */
 #ifndef TILER_SLIDER_H
 #define TILER_SLIDER_H
@@ -52,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TS_VERSION 100          /* 0.1.0 */
+#define TS_VERSION 200          /* 0.2.0 */
 #define TS_CAP_ALIGN 128
 #define TS_MAX_SIZE 16
 #define TS_MAX_TILES 8
@@ -85,7 +89,7 @@ int ts_version(void);
 const char *ts_last_error_string(void);
 
 /* layout queries (pure host arithmetic) */
-int ts_pos_bytes(int n_tiles);
+int ts_pos_bytes(int n_tiles);   /* n_tiles = 0 (a board without tiles): 1, the byte is zero */
 int ts_board_bytes(int size);
 int ts_board_stride(int size);   /* BS: bit index of cell (r,c) in a board = r*BS + c */
 int ts_pos_stride(int size);     /* PS: position byte of a tile at (r,c) = r*PS + c */
@@ -94,7 +98,7 @@ int ts_target_board_bytes(int size); /* bytes per env of the set-goal target boa
 int ts_plane_count(int n_bytes);
 int ts_plane_width(int n_bytes, int k);
 int ts_plane_offset(int n_bytes, int k);
-/* 1 if ts_step has a specialised kernel for (size, n_tiles), else 0 */
+/* 1 if ts_step covers (size, n_tiles): 1 <= size <= 16, 0 <= n_tiles <= 8, else 0 */
 int ts_supported(int size, int n_tiles);
 
 /* ---------------------------------------------------------------------------------------
@@ -103,8 +107,10 @@ int ts_supported(int size, int n_tiles);
  *   d_blocked  u8 [n_envs][size*size]  nonzero = blocked cell
  *   d_tiles    u8 [n_envs][n_tiles][2] (row, col)
  *   d_targets  u8 [n_envs][n_targets][2]
- * Writes walls planes, init + pos position words, targets (ordered: position word, requires
- * n_targets == n_tiles; set: bitboard planes, any n_targets), step_count = 0.
+ * Writes walls planes, init + pos position words, targets (ordered: position word of the first
+ * min(n_targets, n_tiles) targets -- with n_targets != n_tiles the goal can never be met
+ * (state.py:183-184) and the caller passes never_win = 1 to ts_step / ts_goal_check; set:
+ * bitboard planes, any n_targets).  n_tiles may be 0 (d_tiles is then not read).
  * Environments are written at [first_env, first_env + n_envs).
  * ------------------------------------------------------------------------------------- */
 typedef struct ts_encode_args {
@@ -148,6 +154,9 @@ int ts_synth(const ts_synth_args *a, void *stream);
  *             envs finished this step: the positions after the move, before the reset.
  *   never_win: 1 when the goal can never be met (ordered mode with len(targets) !=
  *             len(tiles), state.py:183-184).
+ *   n_tiles = 0: nothing moves (every step is INVALID); won iff the board has no targets either
+ *             (ordered mode: the caller says so through never_win).
+ *   count_bytes = 1 needs max_steps <= 255 with auto_reset, <= 254 without.
  * ------------------------------------------------------------------------------------- */
 typedef struct ts_step_args {
     int32_t size, n_tiles, goal_mode, never_win;
@@ -167,9 +176,12 @@ int ts_step(const ts_step_args *a, void *stream);
  * K3 ts_observe: dense observation, GameState.get_state_array (state.py:188-211).
  *   d_obs f32 [n_envs][size][size][3] (HWC): ch0 blocked, ch1 tile index+1 (ordered mode) or
  *   1 (set mode), ch2 target index+1 or 1.  In set mode targets come from the bitboard.
+ *   n_targets (ordered mode): 0 = as many targets as tiles, d_targets_packed as ts_step reads it;
+ *   k > 0 = k targets in words of ts_pos_bytes(k) bytes per env (a board whose target count
+ *   differs from its tile count, which ts_step's packed word cannot hold); -1 = no targets.
  * ------------------------------------------------------------------------------------- */
 typedef struct ts_observe_args {
-    int32_t size, n_tiles, goal_mode, reserved;
+    int32_t size, n_tiles, goal_mode, n_targets;
     int64_t first_env, n_envs, capacity;
     const uint8_t *d_walls, *d_targets_packed, *d_pos;
     float *d_obs;

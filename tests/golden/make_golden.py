@@ -263,6 +263,52 @@ def misc():
                  multi_color=multi)
         bfs.append(r)
     out["bfs"] = bfs
+    # round 2: slide tables of every board class with blocked START cells in them (the table is
+    # defined there too, state.py:85-118), incl. wide boards
+    tabs2 = []
+    rng = np.random.default_rng(20261018)
+    for S, W in [(7, 9), (8, 14), (9, 20), (12, 36), (14, 40), (15, 50), (16, 64)]:
+        cells = rng.permutation(S * S)[:W]
+        blocked = [(int(c) // S, int(c) % S) for c in cells]
+        st = GameState(S, blocked, [], [], False)
+        tabs2.append({"size": S, "blocked": tolist(blocked), "move_to": st.move_to.tolist()})
+    out["slide_tables_r2"] = tabs2
+    # round 2: degenerate boards the reference accepts -- no tiles (won iff no targets,
+    # tests/test_state.py:40-52, tests/test_environment.py:569-580) and multi-colour boards whose
+    # target count differs from the tile count (never won, state.py:183-184) -- played through
+    # TilerSliderEnv.step with everything it exposes recorded
+    deg = []
+    for S, blocked, tiles, targets, multi, moves, max_steps in [
+        (3, [], [], [], False, "UDLR", 100),
+        (3, [], [], [], True, "UD", 100),
+        (3, [(1, 1)], [], [(0, 0)], False, "UDLRU", 4),
+        (3, [(1, 1)], [], [(0, 0), (2, 2)], True, "LR", 100),
+        (4, [(1, 2)], [(0, 0), (3, 3)], [(0, 3)], True, "RDLURD", 100),
+        (4, [(1, 2)], [(0, 0)], [(0, 3), (3, 3)], True, "RDLU", 3),
+        (5, [(2, 2)], [(0, 0), (4, 4), (0, 4)], [], True, "DRUL", 100),
+        (5, [(2, 2)], [(0, 0), (4, 4)], [(4, 0)], False, "DRUL", 100),
+        (4, [], [(0, 0)], [(3, 0), (3, 0)], False, "DU", 100),
+        (12, [(5, 5), (0, 7)], [(0, 0), (11, 11)], [(11, 0), (11, 0)], False, "DRUL", 100),
+        (12, [(5, 5)], [(0, 0), (3, 3)], [(11, 0)], True, "DRDL", 100),
+        (10, [(5, 5)], [], [(9, 0)], False, "DR", 100),
+        (10, [(5, 5)], [], [], False, "D", 100),
+    ]:
+        env = TilerSliderEnv(size=S, blocked_locations=blocked, initial_locations=list(tiles),
+                             target_locations=list(targets), multi_color=multi, max_steps=max_steps)
+        obs0 = env.reset()
+        rec = {"size": S, "blocked": tolist(blocked), "tiles": tolist(tiles), "targets": tolist(targets),
+               "multi_color": multi, "moves": moves, "max_steps": max_steps, "won_at_reset": bool(env.state.is_won()),
+               "obs_reset": obs0.tolist(), "valid_at_reset": [m.value for m in env.get_valid_moves()], "steps": []}
+        for ch in moves:
+            obs, done, info = env.step(Move.from_char(ch))
+            rec["steps"].append({"move": ch, "positions": tolist(env.state.current_locations), "done": bool(done),
+                                 "state_is_won": bool(env.state.is_won()),
+                                 "info": {k: (bool(v) if isinstance(v, (bool, np.bool_)) else int(v)) for k, v in info.items()},
+                                 "obs": obs.tolist()})
+            if done:
+                break
+        deg.append(rec)
+    out["degenerate"] = deg
     return out
 
 

@@ -97,9 +97,7 @@ def test_gamestate_surface(ts, golden_misc):
                           [(0, 0)] * len(c["tiles"]), False)
         st.move(ts.Move.from_char(c["move"]))
         assert [list(map(int, x)) for x in st.current_locations] == c["after"]
-    for w in golden_misc["win_logic"]:
-        if len(w["tiles"]) == 0 or (w["multi_color"] and len(w["tiles"]) != len(w["targets"])):
-            continue            # outside the supported domain (ValueError), see env.py
+    for w in golden_misc["win_logic"]:      # all nine reference-recorded cases, incl. no tiles / count mismatch
         st = ts.GameState(3, [], [tuple(x) for x in w["tiles"]], [tuple(x) for x in w["targets"]], w["multi_color"])
         assert st.is_won() == w["is_won"], w
     for o in golden_misc["observations"]:
@@ -114,6 +112,48 @@ def test_gamestate_surface(ts, golden_misc):
     cp.move(ts.Move.DOWN)
     assert st.current_locations == [(0, 0), (4, 4)] and cp.current_locations == [(4, 0), (4, 4)]
     assert ts.Move.from_char("u") is ts.Move.UP and ts.Move.from_int(3) is ts.Move.RIGHT and ts.Move.from_char("q") is None
+
+
+def test_slide_tables_of_every_board_class(ts, golden_misc):
+    """GameState.move_to (state.py:75-118) from the step kernels, 7x7 ... 16x16, with blocked
+    start cells in the table (the wide 9..14 slide once kept such a tile in place)."""
+    for t in golden_misc["slide_tables_r2"]:
+        st = ts.GameState(t["size"], [tuple(b) for b in t["blocked"]], [], [], False)
+        assert np.array_equal(st.move_to, np.array(t["move_to"])), t["size"]
+
+
+def test_degenerate_boards_like_the_reference(ts, golden_misc):
+    """Boards without tiles (tests/test_state.py:40-52, tests/test_environment.py:569-580 of the
+    reference: won iff no targets) and multi-colour boards whose target count differs from the
+    tile count (state.py:183-184: played normally, never won), through the drop-in adapter:
+    observations, done, info dicts, positions, is_won and valid moves as the reference recorded."""
+    for rec in golden_misc["degenerate"]:
+        S = rec["size"]
+        env = ts.TilerSliderEnv(size=S, blocked_locations=[tuple(b) for b in rec["blocked"]],
+                                initial_locations=[tuple(t) for t in rec["tiles"]],
+                                target_locations=[tuple(t) for t in rec["targets"]],
+                                multi_color=rec["multi_color"], max_steps=rec["max_steps"])
+        obs = env.reset()
+        assert np.array_equal(obs, np.array(rec["obs_reset"], np.float32).reshape(S, S, 3))
+        assert env.state.is_won() == rec["won_at_reset"]
+        assert [m.value for m in env.get_valid_moves()] == rec["valid_at_reset"]
+        info0 = env.get_info()
+        assert info0["num_tiles"] == len(rec["tiles"]) and info0["num_targets"] == len(rec["targets"])
+        for step in rec["steps"]:
+            obs, done, info = env.step(ts.Move.from_char(step["move"]))
+            assert done == step["done"] and info == step["info"], (rec["size"], rec["tiles"], rec["targets"], step)
+            assert np.array_equal(obs, np.array(step["obs"], np.float32).reshape(S, S, 3))
+            assert [list(map(int, x)) for x in env.state.current_locations] == step["positions"]
+            assert env.state.is_won() == step["state_is_won"]
+        if rec["steps"][-1]["done"]:
+            with pytest.raises(RuntimeError, match="Episode is done"):
+                env.step(ts.Move.UP)
+    # the reference's own two edge-case tests, literally
+    state = ts.GameState(size=3, blocked_locations=[], initial_locations=[], target_locations=[], multi_color=False)
+    assert state.size == 3 and len(state.current_locations) == 0 and state.is_won() == True   # noqa: E712
+    env = ts.TilerSliderEnv(size=3, initial_locations=[], target_locations=[])
+    env.reset()
+    assert env.state.is_won() == True   # noqa: E712
 
 
 def test_constructor_accepts_what_the_reference_accepts(ts):

@@ -154,18 +154,142 @@ def test_set_goal_with_duplicate_and_missing_targets(ts):
     assert want["flags"][0, 0] & F_WON and not (want["flags"][:, 1] & F_WON).any()
 
 
-def test_ordered_goal_length_mismatch_is_rejected(ts):
-    """state.py:183-184: with a different number of targets an ordered goal can never be met; the
-    packed layout has no room for such targets, so the batch is refused (no host fallback)."""
+DEGENERATE = [  # S, T, NT, W, multi, max_steps
+    (5, 0, 0, 3, False, 100), (5, 0, 2, 3, False, 6), (5, 0, 0, 3, True, 100), (5, 0, 3, 0, True, 5),
+    (6, 3, 2, 6, True, 9), (6, 2, 4, 6, True, 100), (4, 1, 0, 2, True, 7), (6, 2, 3, 6, False, 100), (6, 3, 1, 4, False, 12),
+    (12, 0, 0, 20, False, 100), (12, 0, 2, 20, True, 4), (12, 3, 2, 30, True, 100), (12, 2, 5, 30, True, 8),
+    (12, 3, 2, 30, False, 100), (16, 2, 3, 40, False, 10), (9, 1, 1, 10, False, 100),
+]
+
+
+@pytest.mark.parametrize("S,T,NT,W,multi,max_steps", DEGENERATE)
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_degenerate_batches_vs_oracle(ts, S, T, NT, W, multi, max_steps, auto_reset):
+    """Boards without tiles (nothing moves; won iff there are no targets, state.py:183-186) and
+    boards whose target count differs from the tile count (ordered goal: never won,
+    state.py:183-184; set goal: duplicates collapse, state.py:185-186): every field of the step,
+    the observation, the valid-move mask and the goal check against the oracle."""
+    rng = np.random.default_rng(77 * S + 5 * T + NT + (3 if multi else 0))
+    N, K = 515, 24
+    perm = np.argsort(rng.random((N, S * S)), axis=1)
+    blocked = np.zeros((N, S * S), np.uint8)
+    np.put_along_axis(blocked, perm[:, :W], 1, axis=1)
+    tc = perm[:, W:W + T]
+    tiles = np.stack([tc // S, tc % S], -1).astype(np.uint8)
+    gc = perm[:, W + T:W + T + NT].copy()
+    if NT >= 2:
+        gc[::3, 1] = gc[::3, 0]                              # every third board has a duplicate target
+    if NT >= 1 and T >= 1:
+        gc[1::4, 0] = tc[1::4, 0]                             # some targets under tiles
+    targets = np.stack([gc // S, gc % S], -1).astype(np.uint8)
+    actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+    want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=auto_reset)
+    got = run_gpu(ts, S, multi, blocked, tiles, targets, actions, max_steps, auto_reset)
+    assert_same(got, want, f"degenerate S{S} T{T} NT{NT}")
+    env = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=1000)
+    obs, vm, won = env.observe().cpu().numpy(), env.valid_moves().cpu().numpy(), env.goal_check().cpu().numpy()
+    for e in range(0, N, 5):
+        b = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+        st = orc.OracleState(S, b, tiles[e].tolist(), targets[e].tolist(), multi)
+        assert np.array_equal(obs[e], st.get_state_array()), e
+        assert [d for d in range(4) if vm[e] >> d & 1] == st.valid_moves()
+        assert bool(won[e]) == st.is_won()
+    assert tuple(env.target_positions().shape) == ((N, NT, 2) if env.goal_mode == ts.GOAL_ORDERED else (N, S * S))
+
+
+def test_limits_are_value_errors_not_fallbacks(ts):
+    """More than 8 tiles / boards above 16x16 / more than 8 ordered targets on a mismatched board
+    are outside the kernels' domain: ValueError, never a host computation."""
     blocked = np.zeros((1, 9), np.uint8)
-    tiles = np.array([[[0, 0]]], np.uint8)
-    targets = np.array([[[0, 2], [2, 2]]], np.uint8)
-    with pytest.raises(ValueError, match="as many targets as tiles"):
-        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, tiles, targets, True)
-    empty = ts.GameState(3, [], [], [(0, 0)], False)          # recording the board is fine (lazy device state) ...
-    assert empty.size == 3 and len(empty.current_locations) == 0
-    with pytest.raises(ValueError, match="at least one tile"):
-        empty.is_won()                                          # ... computing on it is not
+    with pytest.raises(ValueError):
+        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, np.zeros((1, 9, 2), np.uint8), np.zeros((1, 9, 2), np.uint8), True)
+    with pytest.raises(ValueError):
+        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, np.zeros((1, 1, 2), np.uint8), np.zeros((1, 9, 2), np.uint8), True)
+    with pytest.raises(ValueError):
+        ts.BatchedTilerSliderEnv(17, 1, 4)
+
+
+def test_sub_range_steps_touch_nothing_outside_the_range(ts):
+    """The capacity contract of include/tiler_slider.h: ts_step reads and writes exactly
+    [first_env, first_env + n_envs).  A batch of 1,021 envs (capacity 1,024) has its padding
+    poisoned, and is stepped (a) whole and (b) through the ragged sub-range [0, 510) only -- the
+    envs outside the range, padding included, must stay bit for bit as they were, the envs
+    inside must match the oracle.  Covers the bitboard kernels (4-env groups + the per-env
+    kernel for the ragged end) and the wide kernel."""
+    import ctypes as C
+    for S, T, W, multi, auto_reset in [(6, 4, 8, True, True), (6, 4, 8, False, False), (5, 1, 5, False, True),
+                                       (8, 6, 12, True, False), (12, 8, 36, True, True), (3, 2, 1, True, True)]:
+        N, K, max_steps = 1021, 10, 6
+        rng = np.random.default_rng(S * 100 + T)
+        blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
+        actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+        want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=auto_reset)
+        for n_range in (N, 510, 3):
+            env = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=max_steps,
+                                                       auto_reset=auto_reset, track_terminal=True)
+            cap = env.capacity
+            bufs = {k: getattr(env, k) for k in ("_pos", "_count", "_reward", "_done", "_flags", "_terminal")}
+            poison = {"_pos": 0xA5, "_count": 0x5A, "_reward": -123.5, "_done": 0x77, "_flags": 0, "_terminal": 0xC3}
+            for k, buf in bufs.items():       # the padding envs (flags stay 0: a set DONE bit would mean "frozen")
+                buf[N:] = poison[k]
+            acts = torch.zeros(K, cap, dtype=torch.uint8, device="cuda")
+            acts[:, :N] = torch.as_tensor(actions).cuda()
+            for k in range(K):
+                before = {name: buf.clone() for name, buf in bufs.items()}
+                a = env._step_args(acts[k].data_ptr())
+                a.first_env, a.n_envs = 0, n_range
+                assert ts.lib().ts_step(C.byref(a), torch.cuda.current_stream().cuda_stream) == 0
+                for name, buf in bufs.items():
+                    assert torch.equal(buf[n_range:], before[name][n_range:]), (S, T, name, n_range, k)
+                d = env._done[:n_range].bool()
+                post = env.positions(env._pos[:n_range])
+                if auto_reset:
+                    post = torch.where(d[:, None, None], env.positions(env._terminal[:n_range]), post)
+                assert np.array_equal(post.cpu().numpy(), want["pos"][k][:n_range])
+                assert np.array_equal(env._flags[:n_range].cpu().numpy(), want["flags"][k][:n_range])
+                assert np.array_equal(env._reward[:n_range].cpu().numpy(), want["reward"][k][:n_range])
+
+
+def test_fast_path_without_status_byte(ts):
+    """track_flags=False (auto-reset only): the step stores state, reward and done but no status
+    byte -- one byte less per env-step.  Same positions / reward / done as the tracked batch and
+    the oracle; is_won() comes from the reward."""
+    for S, T, W, multi in [(6, 4, 8, True), (5, 1, 5, False), (12, 8, 36, True), (8, 3, 10, False)]:
+        N, K = 4099, 40
+        kw = dict(seed=31, max_steps=9, auto_reset=True, track_terminal=True)
+        a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, **kw)
+        b = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, track_flags=False, **kw)
+        assert not b.track_flags and b._step_args(b._actions.data_ptr()).d_flags is None
+        g = torch.Generator(device="cuda").manual_seed(8)
+        acts = torch.randint(0, 4, (K, a.capacity), dtype=torch.uint8, device="cuda", generator=g)
+        for k in range(K):
+            a.step(acts[k])
+            b.step(acts[k])
+            assert torch.equal(a.pos, b.pos) and torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
+            assert torch.equal(a.terminal_pos[a.done], b.terminal_pos[b.done]) and torch.equal(a.step_count, b.step_count)
+            assert torch.equal(a.is_won(), b.is_won())
+        with pytest.raises(RuntimeError):
+            b.flags
+    # without auto-reset the done state lives in the status byte: the request is ignored
+    c = ts.BatchedTilerSliderEnv.synthetic(64, 5, 1, 5, False, auto_reset=False, track_flags=False)
+    assert c.track_flags
+
+
+def test_one_byte_counter_boundary(ts):
+    """max_steps 254 / 255: the SWAR counter of a frozen env must not carry into its neighbour
+    (255 without auto-reset therefore uses the 4-byte counter)."""
+    for max_steps, auto_reset in [(254, False), (255, False), (255, True), (254, True)]:
+        S, T, W, N, K = 4, 1, 2, 64, 300
+        rng = np.random.default_rng(max_steps)
+        blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
+        targets[:] = tiles                     # a tile starts on its target: a win needs a move away and back
+        actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+        want = orc.rollout(S, False, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=auto_reset)
+        got = run_gpu(ts, S, False, blocked, tiles, targets, actions, max_steps, auto_reset)
+        assert_same(got, want, f"max_steps {max_steps}")
+    e = ts.BatchedTilerSliderEnv.synthetic(8, 4, 1, 2, False, max_steps=255, auto_reset=False)
+    assert e.count_bytes == 4
+    assert ts.BatchedTilerSliderEnv.synthetic(8, 4, 1, 2, False, max_steps=255, auto_reset=True).count_bytes == 1
 
 
 def test_observation_valid_moves_goal(ts):
@@ -246,49 +370,23 @@ def test_synthetic_rollout_vs_oracle(ts):
             assert np.array_equal(r.cpu().numpy(), want["reward"][k])
 
 
-@pytest.mark.parametrize("S,T,W,multi,auto_reset,max_steps", [(6, 4, 8, True, True, 100), (6, 4, 8, False, False, 11),
-                                                               (5, 1, 5, False, True, 7), (4, 2, 2, True, True, 100),
-                                                               (8, 8, 12, True, True, 100), (6, 3, 4, True, False, 100)])
-def test_pipelined_kernel_matches_direct_kernel_and_oracle(ts, monkeypatch, S, T, W, multi, auto_reset, max_steps):
-    """With TS_STEP_PIPE=1 (the opt-in experiment, switched on for this test only) batches of
-    >= 2^18 envs run the persistent bulk-async kernel (step_kernel_pipe); the same batch stepped
-    through 65,536-env sub-ranges runs the direct kernel -- the default.  Both must agree bit
-    for bit on every array, and the first 2,048 envs must match the oracle.  N is not a
-    multiple of the tile, so the ragged last tile and the padding envs are exercised."""
-    import ctypes as C
-    monkeypatch.setenv("TS_STEP_PIPE", "1")
-    N, K = (1 << 18) + 128 * 5 + 37, 24
-    kw = dict(seed=5, max_steps=max_steps, auto_reset=auto_reset, track_terminal=True)
-    a = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, **kw)
-    b = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, **kw)
-    n_chk = 2048
-    blocked = a.blocked_cells()[:n_chk].cpu().numpy().astype(np.uint8)
-    tiles = a.positions()[:n_chk].cpu().numpy()
-    if a.goal_mode == ts.GOAL_ORDERED:
-        targets = a.target_positions()[:n_chk].cpu().numpy()
-    else:
-        cells = a.target_positions()[:n_chk].cpu().numpy()
-        tc = np.stack([np.flatnonzero(r) for r in cells])
-        targets = np.stack([tc // S, tc % S], -1).astype(np.uint8)
-    g = torch.Generator(device="cuda").manual_seed(3)
-    actions = torch.randint(0, 4, (K, a.capacity), dtype=torch.uint8, device="cuda", generator=g)
-    want = orc.rollout(S, multi, blocked, tiles, targets, actions[:, :n_chk].cpu().numpy(), max_steps=max_steps,
-                       auto_reset=auto_reset)
-    for k in range(K):
-        _, r, d = a.step(actions[k])
-        args = b._step_args(actions[k].data_ptr())
-        for lo in range(0, N, 65536):
-            args.first_env, args.n_envs = lo, min(65536, N - lo)
-            assert ts.lib().ts_step(C.byref(args), torch.cuda.current_stream().cuda_stream) == 0
-        for name in ("_pos", "_count", "_reward", "_done", "_flags"):
-            assert torch.equal(getattr(a, name)[:N], getattr(b, name)[:N]), (name, k)
-        dd = d[:n_chk]
-        post = a.positions()[:n_chk]
-        if auto_reset:
-            post = torch.where(dd[:, None, None], a.positions(a.terminal_pos)[:n_chk], post)
-        assert np.array_equal(post.cpu().numpy(), want["pos"][k])
-        assert np.array_equal(a.flags[:n_chk].cpu().numpy(), want["flags"][k])
-        assert np.array_equal(r[:n_chk].cpu().numpy(), want["reward"][k])
+def test_pipelined_kernel_matches_direct_kernel_and_oracle(ts):
+    """The persistent bulk-async (cp.async.bulk + mbarrier) step kernel is an opt-in experiment that
+    the product library does not carry (-DTS_WITH_PIPE; it measured 5-25 % slower).  A variant
+    library with it is built into variants/ and driven in a subprocess (TS_LIB_PATH, TS_STEP_PIPE=1):
+    batches of >= 2^18 envs stepped by the pipelined kernel against the same batches stepped by the
+    direct kernel through 65,536-env sub-ranges, bit for bit, and against the oracle."""
+    import os
+    import subprocess
+    import sys
+    from tiler_slider_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    variant = _lib.build_variant("pipe", "-DTS_WITH_PIPE")
+    env = dict(os.environ, TS_LIB_PATH=variant, TS_STEP_PIPE="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "pipe_variant_check.py")], env=env,
+                         capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "pipe variant ok" in out.stdout
 
 
 def test_full_size_properties(ts):

@@ -137,6 +137,53 @@ def test_slide_tables(golden_misc):
         assert np.array_equal(ps.move_to, np.array(t["move_to"]))
 
 
+def test_slide_tables_every_board_class_with_blocked_start_cells(golden_misc):
+    """Round-2 fixture: tables of 7x7 ... 16x16 boards; the table is defined for blocked start
+    cells too (state.py:85-118 never looks at the start cell itself)."""
+    for t in golden_misc["slide_tables_r2"]:
+        want = np.array(t["move_to"])
+        st = orc.OracleState(t["size"], t["blocked"], [], [], False)
+        assert np.array_equal(st.move_to, want), t["size"]
+        ps = py_port.PortState(t["size"], [tuple(b) for b in t["blocked"]], [], [], False)
+        assert np.array_equal(ps.move_to, want), t["size"]
+
+
+def _flags_of(step):
+    i = step["info"]
+    return (orc.F_DONE if step["done"] else 0) | (orc.F_WON if i["is_won"] else 0) | \
+        (orc.F_INVALID if i["invalid_move"] else 0) | (orc.F_TIMEOUT if i.get("timeout") else 0)
+
+
+def test_degenerate_boards(golden_misc):
+    """Boards without tiles (won iff no targets: the reference's tests/test_state.py:40-52,
+    tests/test_environment.py:569-580) and multi-colour boards whose target count differs from
+    the tile count (never won, state.py:183-184), as the reference plays them."""
+    for rec in golden_misc["degenerate"]:
+        S, multi = rec["size"], rec["multi_color"]
+        T, NT = len(rec["tiles"]), len(rec["targets"])
+        st = orc.OracleState(S, rec["blocked"], rec["tiles"], rec["targets"], multi)
+        assert st.is_won() == rec["won_at_reset"]
+        assert np.array_equal(st.get_state_array(), np.array(rec["obs_reset"], np.float32).reshape(S, S, 3))
+        assert st.valid_moves() == rec["valid_at_reset"]
+        blocked = np.zeros((1, S * S), np.uint8)
+        for r, c in rec["blocked"]:
+            blocked[0, r * S + c] = 1
+        acts = np.array([[MOVES[s["move"]]] for s in rec["steps"]], np.uint8)
+        got = orc.rollout(S, multi, blocked, np.array(rec["tiles"], np.uint8).reshape(1, T, 2),
+                          np.array(rec["targets"], np.uint8).reshape(1, NT, 2), acts, max_steps=rec["max_steps"])
+        env = py_port.PortEnv(S, [tuple(b) for b in rec["blocked"]], [tuple(t) for t in rec["tiles"]],
+                              [tuple(t) for t in rec["targets"]], multi, rec["max_steps"])
+        env.reset()
+        for k, step in enumerate(rec["steps"]):
+            assert got["flags"][k, 0] == _flags_of(step), (rec, k)
+            assert got["count"][k, 0] == step["info"]["step_count"]
+            assert got["pos"][k, 0].tolist() == step["positions"]
+            obs, done, info = env.step(MOVES[step["move"]])
+            assert done == step["done"] and {k2: (bool(v) if isinstance(v, (bool, np.bool_)) else int(v)) for k2, v in info.items()} == step["info"]
+            assert np.array_equal(obs, np.array(step["obs"], np.float32).reshape(S, S, 3))
+            assert env.state.is_won() == step["state_is_won"]
+
+
 def test_slide_table_known_answers():
     """tests/test_state.py:71-157 style: open 5x5 slides to the edges; a wall stops short."""
     st = orc.OracleState(5, [], [(2, 2)], [(0, 0)], False)

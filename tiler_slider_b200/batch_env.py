@@ -38,14 +38,14 @@ class BatchedTilerSliderEnv:
     def __init__(self, size: int, n_tiles: int, n_envs: int, multi_color: bool = False, *,
                  max_steps: int = 100, auto_reset: bool = False, device: str | torch.device = "cuda",
                  rewards: Sequence[float] = DEFAULT_REWARDS, track_terminal: bool = False,
-                 n_targets: int | None = None):
+                 n_targets: int | None = None, track_flags: bool = True):
         if not torch.cuda.is_available():
             raise _lib.TilerSliderError("BatchedTilerSliderEnv needs a CUDA device (no CPU fallback)")
         self._lib = lib()
         if not 1 <= size <= MAX_SIZE:
             raise ValueError(f"board size {size} outside 1..{MAX_SIZE}")
-        if not 1 <= n_tiles <= MAX_TILES:
-            raise ValueError(f"tile count {n_tiles} outside 1..{MAX_TILES}")
+        if not 0 <= n_tiles <= MAX_TILES:
+            raise ValueError(f"tile count {n_tiles} outside 0..{MAX_TILES}")
         if n_envs < 1:
             raise ValueError("n_envs must be positive")
         if not self._lib.ts_supported(size, n_tiles):
@@ -56,12 +56,17 @@ class BatchedTilerSliderEnv:
         # T == 1 with one target: ordered and set equality coincide; use the cheaper compare
         self.goal_mode = GOAL_ORDERED if (self.multi_color or (self.n_tiles == 1 and self.n_targets == 1)) else GOAL_SET
         # ordered list equality with a length mismatch is never true (state.py:183-184): such a
-        # batch could never report a win and its targets do not fit the packed layout
-        if self.multi_color and self.n_targets != self.n_tiles:
-            raise ValueError("multi-colour batches need as many targets as tiles")
-        self.never_win = False
+        # batch plays normally and never reports a win (never_win); its targets do not fit the
+        # packed word the step kernel compares, so the observation kernel gets them separately
+        self.never_win = self.multi_color and self.n_targets != self.n_tiles
+        if self.never_win and self.n_targets > MAX_TILES:
+            raise ValueError(f"multi-colour boards with {self.n_targets} targets exceed the supported maximum of {MAX_TILES}")
         self.max_steps = int(max_steps)
         self.auto_reset = bool(auto_reset)
+        # the status byte (is_won / invalid_move / timeout / stale) is optional with auto-reset:
+        # reward and done are always written, and without it the step moves 26 instead of 27 bytes
+        # per env (6x6 / 4 tiles); without auto-reset the done state of an env lives in that byte
+        self.track_flags = bool(track_flags) or not self.auto_reset
         self.rewards = tuple(float(x) for x in rewards)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -73,7 +78,7 @@ class BatchedTilerSliderEnv:
         self.board_bytes = self._lib.ts_board_bytes(self.size)
         self.board_stride = self._lib.ts_board_stride(self.size)
         self.pos_stride = self._lib.ts_pos_stride(self.size)
-        self.count_bytes = 1 if self.max_steps <= 255 else 4
+        self.count_bytes = 1 if self.max_steps <= (255 if self.auto_reset else 254) else 4
         cap, dev = self.capacity, self.device
         u8 = torch.uint8
         self.wide = self.size > 8
@@ -88,6 +93,7 @@ class BatchedTilerSliderEnv:
         self._done = torch.zeros(cap, dtype=u8, device=dev)
         self._flags = torch.zeros(cap, dtype=u8, device=dev)
         self._terminal = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev) if track_terminal else None
+        self._obs_targets = None      # ordered targets of a never_win batch, for observe() / target_positions()
         self._scratch_count = None
         self._scratch_flags = None
         self._scratch_reward = None
@@ -160,6 +166,10 @@ class BatchedTilerSliderEnv:
         with torch.cuda.device(dev):
             check(self._lib.ts_encode(C.byref(a), self._stream()), "ts_encode")
             torch.cuda.current_stream().synchronize()   # b, t, g are temporaries
+        if self.never_win:
+            pw = self._lib.ts_pos_bytes(nt)
+            self._obs_targets = torch.zeros(self.capacity, pw, dtype=torch.uint8, device=dev)
+            self._obs_targets[: self.n_envs, :nt] = g[..., 0] * self.pos_stride + g[..., 1]
         self._loaded = True
         self.reset()
 
@@ -188,7 +198,7 @@ class BatchedTilerSliderEnv:
                         auto_reset=int(self.auto_reset if auto_reset is None else auto_reset),
                         d_actions=actions_ptr, r_win=self.rewards[0], r_step=self.rewards[1], r_invalid=self.rewards[2],
                         d_reward=_ptr(self._reward), d_done=None if raw else _ptr(self._done),
-                        d_flags=_ptr(self._flags if flags is None else flags),
+                        d_flags=_ptr(self._flags if flags is None else flags) if (self.track_flags or flags is not None) else None,
                         d_terminal_pos=None if raw else _ptr(self._terminal))
 
     def _stage_actions(self, actions) -> int:
@@ -280,6 +290,8 @@ class BatchedTilerSliderEnv:
         self._require_loaded()
         if h_flags is None and (h_reward is None or h_done is None):
             raise ValueError("step_host needs h_reward and h_done, or h_flags")
+        if h_flags is not None and not self.track_flags:
+            raise ValueError("this batch was built with track_flags=False: there is no status byte to download")
         for t, dt in ((h_actions, torch.uint8), (h_reward, torch.float32), (h_done, torch.uint8), (h_flags, torch.uint8)):
             if t is not None and (t.is_cuda or t.dtype != dt or t.numel() < self.n_envs or not t.is_contiguous()):
                 raise ValueError("step_host needs contiguous host tensors: uint8 actions, float32 reward, uint8 done / flags")
@@ -316,6 +328,8 @@ class BatchedTilerSliderEnv:
     @property
     def flags(self) -> torch.Tensor:
         """uint8[N]: F_DONE | F_WON | F_INVALID | F_TIMEOUT | F_STALE of the last step."""
+        if not self.track_flags:
+            raise RuntimeError("this batch was built with track_flags=False: the step stores reward and done only")
         return self._flags[: self.n_envs]
 
     @property
@@ -337,6 +351,10 @@ class BatchedTilerSliderEnv:
     def is_won(self) -> torch.Tensor:
         """bool[N]: WON bit of the last step (the reference evaluates the goal only after a
         move, environment.py:123; nothing is won straight after reset)."""
+        if not self.track_flags:      # reward = r_win exactly when the step won
+            if self.rewards[0] in self.rewards[1:]:
+                raise RuntimeError("track_flags=False and r_win equals another reward: is_won() cannot be told from the reward")
+            return self.reward == self.rewards[0]
         return (self.flags & F_WON) != 0
 
     def goal_check(self) -> torch.Tensor:
@@ -361,8 +379,8 @@ class BatchedTilerSliderEnv:
         """Unpack a plane-layout bitboard buffer to bool[N, S*S] (load-time / debugging aid)."""
         nb, cap, n = self.board_bytes, self.capacity, self.n_envs
         if self.wide:   # u16 lines: walls [axis][capacity][S rounded up to even] (last plane = rows), targets [capacity][16]
-            per_env = (self.size + 1) // 2 * 2 if walls else 16
-            lines = buf.view(torch.int16).view(-1, cap, per_env)[-1, :n].to(torch.int32) & 0xFFFF
+            per_env = (self.size + 1) // 2 * 2 if walls else 17    # targets: 16 rows + the distinct-target count
+            lines = buf.view(torch.int16).view(-1, cap, per_env)[-1, :n, :16 if not walls else per_env].to(torch.int32) & 0xFFFF
             lead = 1 if walls and self.size <= 14 else 0     # wall lines of S <= 14 start with an edge sentinel
             bits = (lines.unsqueeze(-1) >> (torch.arange(16, device=buf.device) + lead)) & 1
             return bits[:, : self.size, : self.size].reshape(n, self.size * self.size).bool()
@@ -381,7 +399,10 @@ class BatchedTilerSliderEnv:
     def target_positions(self) -> torch.Tensor:
         """Ordered mode: uint8[N,T,2].  Set mode: bool[N,S*S] target cells."""
         if self.goal_mode == GOAL_ORDERED:
-            t = self._targets.view(self.capacity, self.pos_bytes)[: self.n_envs, : self.n_tiles]
+            if self._obs_targets is not None:       # target count != tile count (never_win)
+                t = self._obs_targets[: self.n_envs, : self.n_targets]
+            else:
+                t = self._targets.view(self.capacity, self.pos_bytes)[: self.n_envs, : self.n_tiles]
             return torch.stack((t // self.pos_stride, t % self.pos_stride), dim=-1)
         return self._board_cells(self._targets)
 
@@ -392,9 +413,12 @@ class BatchedTilerSliderEnv:
         if out is None:
             out = torch.empty(n, S, S, 3, dtype=torch.float32, device=self.device)
         # single colour with one tile is stored as an ordered batch: index+1 == 1, same values
-        a = ObserveArgs(size=S, n_tiles=self.n_tiles, goal_mode=self.goal_mode,
+        # a never_win batch draws its ordered targets from their own buffer (count != tile count)
+        nt = 0 if self._obs_targets is None else (self.n_targets or -1)
+        tg = self._targets if self._obs_targets is None else self._obs_targets
+        a = ObserveArgs(size=S, n_tiles=self.n_tiles, goal_mode=self.goal_mode, n_targets=nt,
                         first_env=0, n_envs=n, capacity=self.capacity, d_walls=_ptr(self._walls),
-                        d_targets_packed=_ptr(self._targets), d_pos=_ptr(self._pos), d_obs=_ptr(out))
+                        d_targets_packed=_ptr(tg), d_pos=_ptr(self._pos), d_obs=_ptr(out))
         with torch.cuda.device(self.device):
             check(self._lib.ts_observe(C.byref(a), self._stream()), "ts_observe")
         return out

@@ -22,6 +22,8 @@ cudaError_t observe_dispatch(const ts_observe_args&, cudaStream_t);
 cudaError_t wide_step_dispatch(const ts_step_args&, cudaStream_t);
 cudaError_t wide_valid_dispatch(const ts_valid_args&, cudaStream_t);
 cudaError_t wide_goal_dispatch(const ts_goal_args&, cudaStream_t);
+cudaError_t generic_step_dispatch(const ts_step_args&, cudaStream_t);
+cudaError_t empty_goal_dispatch(const ts_goal_args&, cudaStream_t);
 
 static thread_local char g_err[256] = "ok";
 static int fail(int code, const char* fmt, ...) {
@@ -40,24 +42,12 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 static int check_shape(int size, int n_tiles, int64_t first, int64_t n, int64_t cap) {
     if (size < 1 || size > MAX_SIZE) return fail(TS_E_BAD_SIZE, "size %d outside 1..%d", size, MAX_SIZE);
-    if (n_tiles < 1 || n_tiles > MAX_TILES) return fail(TS_E_BAD_TILES, "n_tiles %d outside 1..%d", n_tiles, MAX_TILES);
+    if (n_tiles < 0 || n_tiles > MAX_TILES) return fail(TS_E_BAD_TILES, "n_tiles %d outside 0..%d", n_tiles, MAX_TILES);
     if (cap >= (int64_t)1 << 33) return fail(TS_E_BAD_CAPACITY, "capacity %lld too large (max 2^33 - 128 envs per call)", (long long)cap);
     if (cap <= 0 || cap % CAP_ALIGN != 0) return fail(TS_E_BAD_CAPACITY, "capacity %lld is not a positive multiple of %d", (long long)cap, CAP_ALIGN);
     if (first < 0 || n < 0 || first % GROUP != 0 || first + n > cap)
         return fail(TS_E_BAD_RANGE, "env range [%lld, %lld) invalid for capacity %lld (first_env must be a multiple of %d)",
                     (long long)first, (long long)(first + n), (long long)cap, GROUP);
-    return 0;
-}
-
-// ---- runtime access to the plane layout (load-time kernels only) -----------------------------
-__device__ __forceinline__ size_t board_byte_addr(int nb, size_t cap, size_t env, int byte) {
-    int off = 0;
-    const int np = plane_count(nb);
-    for (int k = 0; k < np; ++k) {
-        const int w = plane_width(nb, k);
-        if (byte < off + w) return (size_t)off * cap + env * (size_t)w + (size_t)(byte - off);
-        off += w;
-    }
     return 0;
 }
 
@@ -108,10 +98,10 @@ __device__ void store_target_board(uint8_t* d_tb, size_t cap, size_t env, int S,
         int distinct = 0;
         for (int r = 0; r < 16; ++r) distinct += __popc((uint32_t)rows[r]);
         // the wide kernels test "every tile on a target cell"; that is set equality only when
-        // there are exactly T distinct targets -- otherwise the goal is unreachable
-        // (state.py:185-186), encoded as an empty board
-        uint16_t* o = reinterpret_cast<uint16_t*>(d_tb) + env * 16;
-        for (int r = 0; r < 16; ++r) o[r] = distinct == T ? rows[r] : (uint16_t)0;
+        // there are exactly T distinct targets (state.py:185-186): the count travels in word 16
+        uint16_t* o = reinterpret_cast<uint16_t*>(d_tb) + env * WIDE_TARGET_WORDS;
+        for (int r = 0; r < 16; ++r) o[r] = rows[r];
+        o[16] = (uint16_t)distinct;
         return;
     }
     const int nb = board_bytes(S), bs = board_stride(S);
@@ -141,7 +131,7 @@ __global__ void encode_kernel(const ts_encode_args a) {
     const uint8_t* tg = a.d_targets + (size_t)i * NT * 2;
     if (a.goal_mode == TS_GOAL_ORDERED) {
         for (int t = 0; t < pw; ++t)
-            a.d_targets_packed[env * pw + t] = t < NT ? (uint8_t)(tg[2 * t] * ps + tg[2 * t + 1]) : 0;
+            a.d_targets_packed[env * pw + t] = (t < NT && t < T) ? (uint8_t)(tg[2 * t] * ps + tg[2 * t + 1]) : 0;
     } else {
         int cells[MAX_SIZE * MAX_SIZE];
         const int n = NT < MAX_SIZE * MAX_SIZE ? NT : MAX_SIZE * MAX_SIZE;
@@ -216,16 +206,14 @@ int ts_plane_width(int n_bytes, int k) { return plane_width(n_bytes, k); }
 int ts_plane_offset(int n_bytes, int k) { return plane_offset(n_bytes, k); }
 int ts_walls_bytes(int size) { return walls_bytes(size); }
 int ts_target_board_bytes(int size) { return target_board_bytes(size); }
-int ts_supported(int size, int n_tiles) { return size >= 1 && size <= MAX_SIZE && n_tiles >= 1 && n_tiles <= MAX_TILES; }
+int ts_supported(int size, int n_tiles) { return size >= 1 && size <= MAX_SIZE && n_tiles >= 0 && n_tiles <= MAX_TILES; }
 
 int ts_encode(const ts_encode_args* a, void* stream) {
     if (!a) return fail(TS_E_NULL_POINTER, "null args");
     if (int rc = check_shape(a->size, a->n_tiles, a->first_env, a->n_envs, a->capacity)) return rc;
     if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
-    if (a->goal_mode == TS_GOAL_ORDERED && a->n_targets != a->n_tiles)
-        return fail(TS_E_BAD_TILES, "ordered goal needs n_targets == n_tiles (got %d, %d)", a->n_targets, a->n_tiles);
     if (a->n_targets < 0 || a->n_targets > MAX_SIZE * MAX_SIZE) return fail(TS_E_BAD_TILES, "n_targets %d", a->n_targets);
-    if (!a->d_blocked || !a->d_tiles || (!a->d_targets && a->n_targets) || !a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos)
+    if (!a->d_blocked || (!a->d_tiles && a->n_tiles) || (!a->d_targets && a->n_targets) || !a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos)
         return fail(TS_E_NULL_POINTER, "null device pointer");
     if (a->n_envs == 0) return 0;
     const unsigned blocks = (unsigned)((a->n_envs + 127) / 128);
@@ -252,7 +240,8 @@ int ts_step(const ts_step_args* a, void* stream) {
     if (!ts_supported(a->size, a->n_tiles)) return fail(TS_E_UNSUPPORTED, "no step kernel for size %d, n_tiles %d", a->size, a->n_tiles);
     if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return fail(TS_E_BAD_ARGUMENT, "goal_mode %d", a->goal_mode);
     if (a->count_bytes != 1 && a->count_bytes != 4) return fail(TS_E_BAD_ARGUMENT, "count_bytes %d (1 or 4)", a->count_bytes);
-    if (a->count_bytes == 1 && a->max_steps > 255) return fail(TS_E_BAD_ARGUMENT, "max_steps %d needs count_bytes 4", a->max_steps);
+    // 1-byte counters are bumped SWAR, four to a word: a frozen env (auto_reset = 0) resting at 255 would carry into its neighbour
+    if (a->count_bytes == 1 && a->max_steps > (a->auto_reset ? 255 : 254)) return fail(TS_E_BAD_ARGUMENT, "max_steps %d needs count_bytes 4", a->max_steps);
     if (!a->d_walls || !a->d_targets_packed || !a->d_init || !a->d_pos || !a->d_step_count || !a->d_actions || !a->d_reward)
         return fail(TS_E_NULL_POINTER, "null device pointer");
     if (!a->d_done && !a->d_flags) return fail(TS_E_NULL_POINTER, "need d_done or d_flags");
@@ -264,18 +253,29 @@ int ts_step(const ts_step_args* a, void* stream) {
     if (a->n_envs == 0) return 0;
     ts_step_args args = *a;
     if (args.max_steps < 1) args.max_steps = 1;   // step_count >= max_steps holds on the first step either way
-    cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (a->size) {
-        case 1: e = step_dispatch_s1(args, st); break;
-        case 2: e = step_dispatch_s2(args, st); break;
-        case 3: e = step_dispatch_s3(args, st); break;
-        case 4: e = step_dispatch_s4(args, st); break;
-        case 5: e = step_dispatch_s5(args, st); break;
-        case 6: e = step_dispatch_s6(args, st); break;
-        case 7: e = step_dispatch_s7(args, st); break;
-        case 8: e = step_dispatch_s8(args, st); break;
-        default: e = wide_step_dispatch(args, st); break;
+    if (a->n_tiles == 0) return cuda_result(generic_step_dispatch(args, st), "ts_step launch");   // nothing to slide (ts_generic.cu)
+    // the bitboard kernels own whole 4-env groups: the ragged end of the range goes to the generic kernel
+    const int64_t ragged = wide_board(a->size) ? 0 : a->n_envs % GROUP;
+    args.n_envs -= ragged;
+    cudaError_t e = cudaSuccess;
+    if (args.n_envs > 0) {
+        switch (a->size) {
+            case 1: e = step_dispatch_s1(args, st); break;
+            case 2: e = step_dispatch_s2(args, st); break;
+            case 3: e = step_dispatch_s3(args, st); break;
+            case 4: e = step_dispatch_s4(args, st); break;
+            case 5: e = step_dispatch_s5(args, st); break;
+            case 6: e = step_dispatch_s6(args, st); break;
+            case 7: e = step_dispatch_s7(args, st); break;
+            case 8: e = step_dispatch_s8(args, st); break;
+            default: e = wide_step_dispatch(args, st); break;
+        }
+    }
+    if (e == cudaSuccess && ragged) {
+        args.first_env += args.n_envs;
+        args.n_envs = ragged;
+        e = generic_step_dispatch(args, st);
     }
     return cuda_result(e, "ts_step launch");
 }
@@ -297,6 +297,8 @@ int ts_valid_moves(const ts_valid_args* a, void* stream) {
     if (a->n_envs == 0) return 0;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_tiles == 0)      // no tile, no move that changes anything
+        return cuda_result(cudaMemsetAsync(a->d_mask + a->first_env, 0, (size_t)a->n_envs, st), "ts_valid_moves memset");
     switch (a->size) {
         case 1: e = valid_dispatch_s1(*a, st); break;
         case 2: e = valid_dispatch_s2(*a, st); break;
@@ -320,6 +322,7 @@ int ts_goal_check(const ts_goal_args* a, void* stream) {
     if (a->n_envs == 0) return 0;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_tiles == 0) return cuda_result(empty_goal_dispatch(*a, st), "ts_goal_check launch");
     switch (a->size) {
         case 1: e = goal_dispatch_s1(*a, st); break;
         case 2: e = goal_dispatch_s2(*a, st); break;

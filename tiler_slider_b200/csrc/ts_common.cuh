@@ -18,8 +18,8 @@
 //                   goal) use the same stride without sentinels.
 //   S = 7, 8 (compact boards): BS = S, PS = 16, no sentinels.
 //   S >= 9 (wide boards): PS = 16; walls are two records of 4*ceil(S/2) bytes per env, rows and columns
-//                   (walls[axis][env][line] u16), the set-goal target board one sector
-//                   (tboard[env][row] u16); see ts_wide.cu.
+//                   (walls[axis][env][line] u16), the set-goal target board 17 u16 words
+//                   (tboard[env][16 rows + distinct-target count]); see ts_wide.cu.
 //   capacity        allocation stride in envs, a multiple of 128 so that every plane start and
 //                   every 4-env group is 16-byte aligned
 // A thread owns GROUP=4 consecutive envs, so every stream is read with one 32/64/128-bit
@@ -37,7 +37,7 @@ constexpr int CAP_ALIGN = 128;     // capacity granularity (envs)
 constexpr int MAX_SIZE = 16;
 constexpr int MAX_TILES = 8;
 
-__host__ __device__ constexpr int pos_bytes(int T) { return T <= 1 ? 1 : T <= 2 ? 2 : T <= 4 ? 4 : 8; }
+__host__ __device__ constexpr int pos_bytes(int T) { return T <= 1 ? 1 : T <= 2 ? 2 : T <= 4 ? 4 : 8; }   // T = 0: one (zero) byte
 __host__ __device__ constexpr bool padded_board(int S) { return S <= 6; }
 __host__ __device__ constexpr int board_stride(int S) { return padded_board(S) ? S + 1 : S; }
 __host__ __device__ constexpr int pos_stride(int S) { return padded_board(S) ? S + 1 : 16; }
@@ -51,7 +51,11 @@ __host__ __device__ constexpr int wide_line_lead(int S) { return S <= 14 ? 1 : 0
 // wide WALL records: ceil(S/2) pair words (two 16-bit lines each) per env and axis, two axis planes
 __host__ __device__ constexpr int wide_line_words(int S) { return (S + 1) / 2; }
 __host__ __device__ constexpr int walls_bytes(int S) { return wide_board(S) ? 8 * wide_line_words(S) : board_bytes(S); }   // per env
-__host__ __device__ constexpr int target_board_bytes(int S) { return wide_board(S) ? 32 : board_bytes(S); }  // per env, set goal
+// wide set-goal target record: 16 row words + 1 word holding the number of DISTINCT target cells
+// (the wide kernels test "every tile on a target cell", which is set equality exactly when that
+// number equals the tile count; state.py:185-186)
+constexpr int WIDE_TARGET_WORDS = 17;
+__host__ __device__ constexpr int target_board_bytes(int S) { return wide_board(S) ? 2 * WIDE_TARGET_WORDS : board_bytes(S); }  // per env, set goal
 
 // decomposition of nb bytes into planes of width 16 (repeated), 8, 4, 2, 1
 __host__ __device__ constexpr int plane_count(int nb) {
@@ -199,6 +203,19 @@ template <int NB> struct BoardGroup {
         });
     }
 };
+
+// byte `byte` of env `env`'s board inside a plane-layout buffer (runtime sizes: load-time and
+// generic kernels only; the hot kernels use BoardGroup)
+__host__ __device__ __forceinline__ size_t board_byte_addr(int nb, size_t cap, size_t env, int byte) {
+    int off = 0;
+    const int np = plane_count(nb);
+    for (int k = 0; k < np; ++k) {
+        const int w = plane_width(nb, k);
+        if (byte < off + w) return (size_t)off * cap + env * (size_t)w + (size_t)(byte - off);
+        off += w;
+    }
+    return 0;
+}
 
 // integer multiply-add pinned to the FMA pipe (IMAD), keeping it off the saturated ALU pipe
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
@@ -456,8 +473,8 @@ __device__ __forceinline__ void dependent_launch_sync() {
 
 template <typename K, typename A>
 inline void launch_dependent(K kernel, unsigned blocks, unsigned threads, cudaStream_t stream, const A& args) {
-    const char* e = getenv("TS_STEP_PDL");
-    if (e && e[0] == '0') {
+    static const bool plain = [] { const char* e = getenv("TS_STEP_PDL"); return e && e[0] == '0'; }();   // read once
+    if (plain) {
         kernel<<<blocks, threads, 0, stream>>>(args);
         return;
     }

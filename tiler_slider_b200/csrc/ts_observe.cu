@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_a
         bool wall, tgt = false;
         if constexpr (wide_board(S)) {
             wall = (reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * (2 * wide_line_words(S)) + r] >> (c + wide_line_lead(S))) & 1;   // plane 1 = rows
-            if (!ordered) tgt = (reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * 16 + r] >> c) & 1;
+            if (!ordered) tgt = (reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * WIDE_TARGET_WORDS + r] >> c) & 1;
         } else {
             const int bit = r * board_stride(S) + c;
             wall = (load_board_elem<NB>(a.d_walls, cap, env) >> bit) & 1ull;
@@ -57,16 +57,23 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_a
         if (wall) stage[j * 3] = 1.0f;
         if (tgt) stage[j * 3 + 2] = 1.0f;
     }
-    // tiles and ordered targets: one thread per env, ascending index (later overwrites earlier)
+    // tiles and ordered targets: one thread per env, ascending index (later overwrites earlier).
+    // Ordered targets: n_targets = 0 means "as many as tiles, packed like the position word";
+    // otherwise (target count != tile count: a board that can never be won, state.py:183-184)
+    // d_targets_packed holds pos_bytes(n_targets)-byte words of n_targets targets, -1 = none.
+    const int NT = a.n_targets == 0 ? T : (a.n_targets < 0 ? 0 : a.n_targets);
+    const int tpw = pos_bytes(NT);
     for (int e = threadIdx.x; e < n_here; e += OBS_THREADS) {
         const size_t env = (size_t)(a.first_env + env0 + e);
         const uint8_t* pp = a.d_pos + env * pw;
-        const uint8_t* tp = a.d_targets_packed + env * pw;
         float* img = stage + e * PER_ENV;
         for (int k = 0; k < T; ++k) {
             const int b = pp[k];
             img[((b / pos_stride(S)) * S + b % pos_stride(S)) * 3 + 1] = ordered ? (float)(k + 1) : 1.0f;
-            if (ordered) {
+        }
+        if (ordered) {
+            const uint8_t* tp = a.d_targets_packed + env * tpw;
+            for (int k = 0; k < NT; ++k) {
                 const int t = tp[k];
                 img[((t / pos_stride(S)) * S + t % pos_stride(S)) * 3 + 2] = (float)(k + 1);
             }

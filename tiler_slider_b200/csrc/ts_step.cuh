@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     fill_dir_tab<S>(dir_tab);
     // 32-bit group index: every address below is base + g * constant, one IMAD.WIDE each
     // (ts_step rejects capacities of 2^32 groups or more)
-    const uint32_t n_groups = (uint32_t)((a.n_envs + GROUP - 1) / GROUP);
+    // whole 4-env groups only: ts_step hands the ragged end of a range (n_envs % 4 envs) to
+    // generic_step_kernel (ts_generic.cu), so nothing outside [first_env, first_env + n_envs) is touched
+    const uint32_t n_groups = (uint32_t)(a.n_envs / GROUP);
     uint32_t g = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (g >= n_groups) return;
     g += (uint32_t)(a.first_env / GROUP);
@@ -227,6 +229,9 @@ __global__ void __launch_bounds__(STEP_THREADS, (step_min_blocks<S, T, GOAL, AR,
     step_group<S, T, GOAL, AR, CW>(a, g, in, dir_tab);
 }
 
+// ---- OPT-IN experiment, compiled only with -DTS_WITH_PIPE (make EXTRA=-DTS_WITH_PIPE OUT=...): the
+// product library does not carry it (it doubled the size of the .so for a kernel measured slower).
+#ifdef TS_WITH_PIPE
 // ---- pipelined kernel: persistent CTAs, bulk-async (TMA 1-D) staging through shared memory -----
 // A tile is PIPE_THREADS groups (4*PIPE_THREADS envs).  Every input stream of a tile is one
 // contiguous run of bytes in HBM (env-innermost planes), so one elected thread fetches a whole
@@ -440,8 +445,10 @@ inline bool launch_step_pipe(const ts_step_args& a, cudaStream_t stream) {
 inline bool use_pipe(const ts_step_args& a) {
     const char* e = getenv("TS_STEP_PIPE");     // read per call: tests switch it on for one test only
     const bool enabled = e && e[0] == '1';
-    return enabled && a.count_bytes == 1 && a.first_env % CAP_ALIGN == 0 && a.n_envs >= (int64_t)1 << 18;
+    // whole 128-env tiles only: the kernel steps every env of a tile it touches
+    return enabled && a.count_bytes == 1 && a.first_env % CAP_ALIGN == 0 && a.n_envs % CAP_ALIGN == 0 && a.n_envs >= (int64_t)1 << 18;
 }
+#endif  // TS_WITH_PIPE
 
 template <typename K>
 inline void launch_direct(K kernel, const ts_step_args& a, unsigned blocks, cudaStream_t stream) {
@@ -451,10 +458,12 @@ inline void launch_direct(K kernel, const ts_step_args& a, unsigned blocks, cuda
 template <int S, int T, int GOAL>
 inline void launch_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_t stream) {
     const bool ar = a.auto_reset != 0, narrow = a.count_bytes == 1;
+#ifdef TS_WITH_PIPE
     if (use_pipe(a)) {
         const bool ok = ar ? launch_step_pipe<S, T, GOAL, true>(a, stream) : launch_step_pipe<S, T, GOAL, false>(a, stream);
         if (ok) return;
     }
+#endif
     if (ar && narrow) launch_direct(step_kernel<S, T, GOAL, true, 1>, a, blocks, stream);
     else if (ar) launch_direct(step_kernel<S, T, GOAL, true, 4>, a, blocks, stream);
     else if (narrow) launch_direct(step_kernel<S, T, GOAL, false, 1>, a, blocks, stream);
@@ -463,7 +472,7 @@ inline void launch_step_goal(const ts_step_args& a, unsigned blocks, cudaStream_
 
 template <int S, int T>
 inline cudaError_t launch_step(const ts_step_args& a, cudaStream_t stream) {
-    const size_t n_groups = (size_t)((a.n_envs + GROUP - 1) / GROUP);
+    const size_t n_groups = (size_t)(a.n_envs / GROUP);          // the caller passes whole groups (ts_step splits off the rest)
     const unsigned blocks = (unsigned)((n_groups + STEP_THREADS - 1) / STEP_THREADS);
     if (blocks == 0) return cudaSuccess;
     if (a.goal_mode == TS_GOAL_ORDERED) launch_step_goal<S, T, TS_GOAL_ORDERED>(a, blocks, stream);

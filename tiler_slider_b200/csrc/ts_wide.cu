@@ -24,7 +24,7 @@
 //                        pick their axis independently, nearly every line of BOTH planes is still
 //                        touched, so what counts is the footprint: records hold only the
 //                        ceil(S/2) pair words a board of this size has (24 bytes for 12x12).
-//   tboard[env][row]     u16 target cells (set goal only)
+//   tboard[env][17]      u16: 16 rows of target cells + the number of distinct targets (set goal only)
 //   position byte        row*16 + col
 // Thread = one env.  The 16 line words of the chosen orientation and the occupancy lines
 // built from the tile positions live in shared memory as [word][thread] columns: a thread
@@ -205,12 +205,14 @@ __device__ __forceinline__ void slide_wide(WideSmem& sm, uint32_t (&q)[(T + 3) /
     if constexpr (T % 4 != 0) q[PR - 1] &= 0xFFFFFFFFu >> (8 * (4 - T % 4));   // keep unused bytes zero
 }
 
-// set goal: every tile stands on a target cell (ts_encode guarantees the target board is empty
-// unless it has exactly T distinct cells, so this is set equality; state.py:185-186)
+// set goal (state.py:185-186): every tile stands on a target cell AND the board has exactly T
+// distinct target cells (word 16 of the record, written by ts_encode / ts_synth) -- tiles are on
+// distinct cells, so the two together are set equality.  The record keeps the true target cells
+// whatever their number: ts_observe draws channel 2 from it.
 template <int T>
 __device__ __forceinline__ bool on_targets_wide(const uint32_t (&q)[(T + 3) / 4], const uint8_t* tboard, size_t env) {
-    const uint16_t* rows = reinterpret_cast<const uint16_t*>(tboard) + env * 16;
-    bool all = true;
+    const uint16_t* rows = reinterpret_cast<const uint16_t*>(tboard) + env * WIDE_TARGET_WORDS;
+    bool all = __ldg(rows + 16) == (uint16_t)T;
     static_for<0, T>([&](auto I) {
         constexpr int i = decltype(I)::value;
         const uint32_t b = byte_of<i % 4>(q[i / 4]);

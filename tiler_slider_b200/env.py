@@ -10,11 +10,12 @@ through the C-ABI.  Only the Python exceptions of step() (RuntimeError after don
 TypeError on a non-enum action; environment.py:113-117) and the info dict are assembled on
 the host, from the flag byte the step kernel returns.
 
-Limits (ValueError): board size <= 16, 1..8 tiles, well-formed puzzles only (distinct tiles,
-none on a blocked cell; outside that domain the reference itself is erratic), and
-in multi-colour mode as many targets as tiles (with a different count the reference can never
-report a win, state.py:183-184).  Nothing is ever computed on the host: there is no CPU
-fallback behind these classes.
+Limits (ValueError): board size <= 16, 0..8 tiles, well-formed puzzles only (distinct tiles,
+none on a blocked cell; outside that domain the reference itself is erratic).
+Boards without tiles (won iff there are no targets either) and multi-colour boards whose target
+count differs from their tile count (they play normally and never win, state.py:183-184) behave
+as in the reference.  Nothing is ever computed on the host: there is no CPU fallback behind
+these classes.
 """
 from __future__ import annotations
 
@@ -60,10 +61,6 @@ class GameState:
         shapes the kernels do not cover raise ValueError when the first move / goal check /
         observation is asked for."""
         if self._batch_obj is None:
-            if len(self._initial) == 0:
-                raise ValueError("a board needs at least one tile (the CUDA path has nothing to move otherwise)")
-            if self.multi_color and len(self.target_locations) != len(self._initial):
-                raise ValueError("multi-colour boards need as many targets as tiles")
             p = Puzzle(self.size, self._blocked, [(int(r), int(c)) for r, c in self._initial],
                        [(int(r), int(c)) for r, c in self.target_locations], bool(self.multi_color))
             self._batch_obj = BatchedTilerSliderEnv.from_puzzles([p], max_steps=self._max_steps, auto_reset=False,
@@ -121,8 +118,9 @@ class GameState:
             blocked = np.tile(self.is_blocked.reshape(1, n).astype(np.uint8), (n, 1))
             cells = np.arange(n)
             tiles = np.stack([cells // S, cells % S], axis=-1).astype(np.uint8).reshape(n, 1, 2)
-            # (the table is defined for blocked start cells too; the kernel ignores the wall
-            # bit under a tile, as the reference's sweeps do)
+            # the table is defined for blocked start cells too: the reference's sweeps never look at
+            # the start cell itself (state.py:85-118), so probe i runs on a board whose cell i is open
+            blocked[cells, cells] = 0
             probe = BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, tiles.copy(), False, device=self._device)
             table = np.zeros((S, S, 4, 2), dtype=int)
             for d in range(4):
