@@ -92,8 +92,8 @@ def workload_config(cfg: Config, n_gpus: int, envs_per_gpu: int, extra: dict | N
            "envs_total": envs_per_gpu * n_gpus, "max_steps": MAX_STEPS, "auto_reset": True,
            "outputs": "next state (packed positions), reward f32, done u8 per env-step (status byte not stored: track_flags=False)",
            "algorithmic_bytes_per_env_step": cfg.algo_bytes,
-           "l2_policy": (f"inputs larger than L2 ({ws / 1e6:.0f} MB of state+io per step vs 126 MB L2); no flush needed"
-                         if ws > 2 * L2_BYTES else
+           "l2_policy": (f"inputs larger than L2 ({ws / 1e6:.0f} MB of algorithmic state+io per step vs 126 MB L2); no flush needed"
+                         if ws > L2_BYTES else
                          f"working set {ws / 1e6:.0f} MB per step fits the 126 MB L2: steps run L2-resident (stated, not flushed)"),
            "parallelism": f"env-index sharding x{n_gpus}, no collective on the step path"}
     if extra:
@@ -207,7 +207,7 @@ def parity_check(ts, dev, cfg: Config, n_envs: int = 8192, steps: int = 128) -> 
         bad += int((env.flags.cpu().numpy() != want["flags"][k]).sum())
         bad += int((r.cpu().numpy() != want["reward"][k]).sum())
         _, rf, df = fast.step(actions[k])
-        fast_bad += int((~torch.equal(fast.pos, env.pos)) + (~torch.equal(rf, r)) + (~torch.equal(df, d)))
+        fast_bad += int(not torch.equal(fast.pos, env.pos)) + int(not torch.equal(rf, r)) + int(not torch.equal(df, d))
     # K3 / valid-move mask of the states the rollout ended in (first n_obs envs), against the oracle
     n_obs = min(n_envs, 1024)
     obs = env.observe()[:n_obs].cpu().numpy()
@@ -492,7 +492,7 @@ class Runner:
                          "algorithmic_bytes_per_successor": 42, "peak_source": self.peak_source}}
         del solver
         torch.cuda.empty_cache()
-        if hasattr(ts.bfs if hasattr(ts, "bfs") else object, "LocalBfs") or _has_local_bfs():
+        if _has_local_bfs():
             from tiler_slider_b200.bfs import LocalBfs
             local = LocalBfs(table)
             resl, (coldl, warml) = run(local)
