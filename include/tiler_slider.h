@@ -312,6 +312,48 @@ int ts_bfs_levels(const ts_bfs_args *a, int32_t first_depth, int32_t n_levels, u
                   uint64_t *succ, int64_t *lvl, int64_t frontier_capacity, int64_t known_frontier, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K6 ts_bfs_local: breadth-first search of many small puzzles, one CTA per puzzle, on chip
+ * (csrc/ts_bfs_local.cu).  Same successor function, goal test, canonical states and result
+ * definitions as the hash-partitioned search above; boards of size <= 8 with 1..4 tiles.
+ * The visited set of a puzzle is a bitmap in shared memory over the perfect hash
+ * state -> sum(rank(tile i) * F^i), F = free cells of the puzzle, rank = index of a cell among
+ * them; the frontier queue holds `queue_smem` states in shared memory and spills to
+ * d_spill[cta][spill_per_cta].  Persistent grid: CTAs draw puzzles from the ticket counter.
+ *   d_puzzle_ids       optional: search puzzles d_puzzle_ids[0 .. n_puzzles) instead of 0 .. n_puzzles-1
+ *   d_status[pid]      0 searched; 1 F^T bits exceed bitmap_words*32; 2 spill slab exhausted; 3 deeper
+ *                      than 255 levels -- for != 0 nothing else of the puzzle is valid (search it
+ *                      with the hash-partitioned path)
+ *   d_states_per_puzzle[pid], d_solve_depth[pid] (-1: no goal within max_depth)
+ *   d_levels[d]        += new states at depth d over the searched puzzles (n_levels >= 256 entries)
+ *   d_counters         [0] ticket (zero on entry), [1] += successors generated, [3] = max(depth reached)
+ *   d_lengths / d_moves / d_parent_scratch  optional shortest move string per puzzle (0..3, root
+ *                      first; length -1: unsolved or longer than max_moves); d_parent_scratch holds
+ *                      grid * (queue_smem + spill_per_cta) words
+ * ts_bfs_local_smem_bytes: dynamic shared memory of a launch with these arguments;
+ * ts_bfs_local_ctas_per_sm: resident CTAs per SM and the SM count, to size the grid.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ts_bfs_local_args {
+    int32_t size, n_tiles, goal_mode, never_win;
+    int64_t n_puzzles, puzzle_capacity;
+    const uint8_t *d_walls, *d_targets_packed, *d_init;
+    const int32_t *d_puzzle_ids;
+    int32_t max_depth, bitmap_words, queue_smem, n_levels;
+    uint32_t *d_spill;
+    int64_t spill_per_cta;
+    uint32_t *d_parent_scratch;
+    int64_t *d_states_per_puzzle;
+    int32_t *d_solve_depth, *d_status;
+    int64_t *d_levels;
+    uint64_t *d_counters;
+    uint8_t *d_moves;
+    int32_t *d_lengths;
+    int64_t max_moves;
+} ts_bfs_local_args;
+int ts_bfs_local_smem_bytes(const ts_bfs_local_args *a);
+int ts_bfs_local_ctas_per_sm(const ts_bfs_local_args *a, int *ctas_per_sm, int *n_sm);
+int ts_bfs_local(const ts_bfs_local_args *a, int grid, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * ts_step_host: the same step through HOST buffers (the call a host-side driver makes):
  * h_actions (pinned) -> device, ts_step, reward/done -> h_reward/h_done (pinned), pipelined in
  * chunks over the context's streams; returns after everything has landed.

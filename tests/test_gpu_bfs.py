@@ -170,3 +170,138 @@ def test_level_corpus_on_gpu(ts):
             assert _replay((S, p.blocked_locations, p.initial_locations, p.target_locations, multi), sol) == [depth]
             n_checked += 1
     assert n_checked == 400
+
+
+# ---- K6: one CTA per puzzle, visited bitmap in shared memory (LocalBfs) --------------------------
+def _oracle_batch(S, multi, blocked, tiles, targets):
+    states, depths, levels = [], [], {}
+    for e in range(len(blocked)):
+        b = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+        ns, lv, depth, _ = orc.OracleState(S, b, tiles[e].tolist(), targets[e].tolist(), multi).bfs(max_states=1 << 20)
+        states.append(ns)
+        depths.append(depth)
+        for d, c in enumerate(lv):
+            levels[d] = levels.get(d, 0) + c
+    return states, depths, [levels[d] for d in range(len(levels))]
+
+
+def test_local_bfs_known_answers(ts, golden_misc):
+    """The on-chip search on the known answers (29 / 558 / 950 / 51 states, depths
+    1 / 8 / 13 / 7), one puzzle at a time and with paths."""
+    from tiler_slider_b200.bfs import LocalBfs
+    for b in golden_misc["bfs"]:
+        res = LocalBfs([puzzle_of(ts, b)]).solve(with_paths=True)
+        assert res.fallback_puzzles == 0
+        assert (res.n_states, res.levels, res.solve_depth) == (b["n_states"], b["levels"], b["solve_depth"]), b["name"]
+        assert res.states_per_puzzle.tolist() == [b["n_states"]] and res.generated == 4 * b["n_states"]
+        sol = res.solutions[0]
+        if b["solve_depth"] < 0:
+            assert sol is None
+        else:
+            assert len(sol) == b["solve_depth"]
+            assert _replay((b["size"], b["blocked"], b["tiles"], b["targets"], b["multi_color"]), sol) == [len(sol)]
+
+
+@pytest.mark.parametrize("S,T,W,multi,n", [(4, 2, 3, True, 48), (4, 3, 2, False, 32), (5, 2, 5, False, 32), (6, 3, 9, True, 24),
+                                            (3, 4, 1, True, 32), (7, 2, 12, True, 16), (8, 2, 20, False, 16), (5, 1, 3, False, 40),
+                                            (6, 4, 10, False, 24), (6, 4, 8, True, 96), (8, 3, 30, True, 12), (2, 2, 0, False, 8),
+                                            (1, 1, 0, False, 4)])
+def test_local_bfs_random_batches_vs_oracle(ts, S, T, W, multi, n):
+    from tiler_slider_b200.bfs import LocalBfs
+    from tests.helpers import random_puzzles
+    rng = np.random.default_rng(S * 100 + T + 7)
+    blocked, tiles, targets = random_puzzles(rng, n, S, T, W)
+    table = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi)
+    res = LocalBfs(table).solve(with_paths=True)
+    want_states, want_depth, want_levels = _oracle_batch(S, multi, blocked, tiles, targets)
+    assert res.fallback_puzzles == 0
+    assert res.states_per_puzzle.tolist() == want_states
+    assert res.solve_depth_per_puzzle.tolist() == want_depth
+    assert res.levels == want_levels and res.generated == 4 * sum(want_states)
+    for e in range(n):
+        sol = res.solutions[e]
+        if want_depth[e] < 0:
+            assert sol is None
+        else:
+            bl = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+            assert len(sol) == want_depth[e]
+            assert _replay((S, bl, tiles[e].tolist(), targets[e].tolist(), multi), sol)[:1] == [want_depth[e]]
+
+
+def test_local_bfs_agrees_with_hash_partitioned_search(ts):
+    """4,096 benchmark-shape puzzles (a few of them outgrow the shared-memory part of the queue and
+    spill to HBM): per-puzzle state counts, solve depths, the level histogram and the successor
+    count must equal the hash-partitioned search; also with a depth limit, and in set-goal mode."""
+    from tiler_slider_b200.bfs import BfsSolver, LocalBfs
+    for multi, n in ((True, 4096), (False, 1024)):
+        table = ts.BatchedTilerSliderEnv.synthetic(n, 6, 4, 8, multi, seed=1004)
+        for kw in (dict(), dict(max_depth=7), dict(max_depth=1)):
+            a = BfsSolver(table, table_capacity=1 << 26).solve(**kw)
+            loc = LocalBfs(table)
+            b = loc.solve(**kw)
+            assert b.fallback_puzzles == 0 and loc.plan()["ctas_per_sm"] >= 2
+            assert (a.n_states, a.levels, a.solve_depth, a.generated) == (b.n_states, b.levels, b.solve_depth, b.generated), (multi, kw)
+            assert torch.equal(a.states_per_puzzle, b.states_per_puzzle)
+            assert torch.equal(a.solve_depth_per_puzzle.to(torch.int32), b.solve_depth_per_puzzle)
+        if multi:
+            assert int(b.states_per_puzzle.max()) >= 1  # (depth-limited run)
+            full = LocalBfs(table).solve()
+            assert int(full.states_per_puzzle.max()) > loc.plan()["queue_smem"]      # the spill path was exercised
+
+
+def test_local_bfs_queue_spill_and_fallback(ts):
+    """With only 64 queue entries in shared memory nearly every state of every puzzle goes through
+    the HBM spill slab (paths included).  With two walls the state space (34^4 bits = 167 KB) does
+    not fit the bitmap of two CTAs per SM: the planner drops to one CTA per SM; asked for more than
+    fit, the puzzles are searched by the hash-partitioned path instead (fallback), same answers."""
+    from tiler_slider_b200.bfs import BfsSolver, LocalBfs
+    batch = ts.BatchedTilerSliderEnv.synthetic(300, 6, 4, 8, True, seed=5)
+    ref = BfsSolver(batch, table_capacity=1 << 22).solve(with_paths=True)
+    tiny = LocalBfs(batch, queue_smem=64)
+    res = tiny.solve(with_paths=True)
+    assert tiny.plan()["queue_smem"] == 64 and res.fallback_puzzles == 0
+    assert torch.equal(res.states_per_puzzle, ref.states_per_puzzle) and res.levels == ref.levels
+    assert torch.equal(res.solve_depth_per_puzzle, ref.solve_depth_per_puzzle.to(torch.int32))
+    assert [None if x is None else len(x) for x in res.solutions] == [None if x is None else len(x) for x in ref.solutions]
+    blocked, tiles, targets = batch.blocked_cells().cpu().numpy(), batch.positions().cpu().numpy(), batch.target_positions().cpu().numpy()
+    for e in range(0, 300, 7):
+        if res.solutions[e] is not None:
+            bl = [(c // 6, c % 6) for c in np.flatnonzero(blocked[e])]
+            assert _replay((6, bl, tiles[e].tolist(), targets[e].tolist(), True), res.solutions[e])[:1] == [len(res.solutions[e])]
+    few_walls = ts.BatchedTilerSliderEnv.synthetic(64, 6, 4, 2, True, seed=9)      # F = 34: 34^4 bits = 167 KB
+    want = BfsSolver(few_walls, table_capacity=1 << 25).solve()
+    one = LocalBfs(few_walls)
+    got = one.solve()
+    assert one.plan()["ctas_per_sm"] == 1 and got.fallback_puzzles == 0
+    forced = LocalBfs(few_walls, ctas_per_sm=2)                                     # does not fit twice per SM
+    assert forced.plan() is None
+    fb = forced.solve()
+    assert fb.fallback_puzzles == 64
+    for r in (got, fb):
+        assert torch.equal(r.states_per_puzzle, want.states_per_puzzle) and r.levels == want.levels
+        assert torch.equal(r.solve_depth_per_puzzle.to(torch.int32), want.solve_depth_per_puzzle.to(torch.int32))
+
+
+def test_local_bfs_level_corpus(ts):
+    """The reference's 400 real levels through the on-chip search, with shortest solutions."""
+    import os
+    from tiler_slider_b200.bfs import LocalBfs
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels_400.txt")
+    puzzles = ts.load_puzzle_file(path)
+    groups = {}
+    for p in puzzles:
+        groups.setdefault((p.size, len(p.initial_locations), p.multiple_colors), []).append(p)
+    n_checked = 0
+    for (S, T, multi), ps in groups.items():
+        loc = LocalBfs(ps)
+        res = loc.solve(with_paths=True)
+        assert res.fallback_puzzles == 0 and loc.plan()["ctas_per_sm"] >= 4      # tiny bitmaps: many CTAs per SM
+        for i, p in enumerate(ps):
+            st = orc.OracleState(S, p.blocked_locations, p.initial_locations, p.target_locations, multi)
+            n, _, depth, _ = st.bfs()
+            assert int(res.states_per_puzzle[i]) == n and int(res.solve_depth_per_puzzle[i]) == depth
+            sol = res.solutions[i]
+            assert sol is not None and len(sol) == depth
+            assert _replay((S, p.blocked_locations, p.initial_locations, p.target_locations, multi), sol) == [depth]
+            n_checked += 1
+    assert n_checked == 400

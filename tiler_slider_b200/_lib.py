@@ -81,6 +81,16 @@ class BfsArgs(C.Structure):
                 ("d_n_items", _vp), ("n_items_scale", _i64)]
 
 
+class BfsLocalArgs(C.Structure):
+    _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("never_win", _i32),
+                ("n_puzzles", _i64), ("puzzle_capacity", _i64),
+                ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_puzzle_ids", _vp),
+                ("max_depth", _i32), ("bitmap_words", _i32), ("queue_smem", _i32), ("n_levels", _i32),
+                ("d_spill", _vp), ("spill_per_cta", _i64), ("d_parent_scratch", _vp),
+                ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_status", _vp),
+                ("d_levels", _vp), ("d_counters", _vp), ("d_moves", _vp), ("d_lengths", _vp), ("max_moves", _i64)]
+
+
 # every symbol include/tiler_slider.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ts_version": (C.c_int, []),
@@ -109,6 +119,9 @@ SYMBOLS = {
     "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_traceback": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_local_smem_bytes": (C.c_int, [C.POINTER(BfsLocalArgs)]),
+    "ts_bfs_local_ctas_per_sm": (C.c_int, [C.POINTER(BfsLocalArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ts_bfs_local": (C.c_int, [C.POINTER(BfsLocalArgs), C.c_int, _vp]),
     "ts_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "ts_host_ctx_destroy": (C.c_int, [_vp]),
     "ts_step_host": (C.c_int, [_vp, C.POINTER(StepArgs), _vp, _vp, _vp, _vp, _i64]),

@@ -30,8 +30,8 @@ from typing import Sequence
 import torch
 import torch.distributed as dist
 
-from ._lib import BfsArgs, check, lib
-from .batch_env import BatchedTilerSliderEnv
+from ._lib import BfsArgs, BfsLocalArgs, check, lib
+from .batch_env import BatchedTilerSliderEnv, shard_range
 from .puzzle import Puzzle
 
 NONE = -1                       # TS_BFS_NONE as int64
@@ -48,6 +48,7 @@ class BfsResult:
     generated: int = 0                         # successors generated (state x move), all ranks
     per_level_seconds: list[float] = field(default_factory=list)
     solutions: list[str | None] | None = None  # with_paths: a shortest move string per puzzle ('UDLR'), None if unsolved
+    fallback_puzzles: int = 0                  # LocalBfs: puzzles that did not fit on chip and went through the hash-partitioned search
 
 
 @dataclass
@@ -565,6 +566,159 @@ class BfsSolver:
             solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
         return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
                          solve_depth_per_puzzle=depth_pp, generated=generated, solutions=solutions)
+
+
+class LocalBfs:
+    """Batched BFS with one CTA per puzzle and the visited set in shared memory (K6,
+    csrc/ts_bfs_local.cu): for batches of small puzzles, which is what the domain offers (a 6x6
+    board with 4 tiles and 8 walls has 3,300 reachable states on average, the reference's real
+    levels 51-950).  Several ranks: the puzzles are sharded by index (`shard_range`), every rank
+    searches its shard with no exchange at all, and the per-puzzle results are combined once at
+    the end.  A puzzle that does not fit on chip (state space above the shared-memory bitmap,
+    more than 255 levels) is searched by the hash-partitioned `BfsSolver` instead.  Same result
+    definitions as BfsSolver; boards of size <= 8 with 1..4 tiles."""
+
+    N_LEVELS = 256
+    SMEM_PER_SM = 228 * 1024
+    STATIC_SMEM = 4 * 1024          # the kernel's static shared memory + the per-CTA reservation
+    MAX_SCRATCH_BYTES = 4 << 30
+
+    def __init__(self, puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv, *, device="cuda", group=None,
+                 ctas_per_sm: int | None = None, queue_smem: int | None = None, fallback_table_capacity: int = 1 << 24):
+        table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else \
+            BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
+        if table.size > 8 or not 1 <= table.n_tiles <= 4:
+            raise ValueError("the on-chip BFS covers board sizes up to 8 with 1 to 4 tiles")
+        self.t, self.lib, self.device, self.group = table, lib(), table.device, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.want_ctas = ctas_per_sm
+        self.want_queue = queue_smem        # cap on the queue entries kept in shared memory (tests: force the spill path)
+        self.fallback_table_capacity = fallback_table_capacity
+        self._plan = None
+        self._scratch: dict[str, torch.Tensor] = {}
+
+    def _args(self, **kw) -> BfsLocalArgs:
+        t = self.t
+        base = dict(size=t.size, n_tiles=t.n_tiles, goal_mode=t.goal_mode, never_win=int(t.never_win),
+                    puzzle_capacity=t.capacity, d_walls=t._walls.data_ptr(), d_targets_packed=t._targets.data_ptr(),
+                    d_init=t._init.data_ptr(), n_levels=self.N_LEVELS)
+        base.update(kw)
+        return BfsLocalArgs(**base)
+
+    def plan(self) -> dict | None:
+        """Shared-memory split and grid of the launch: the bitmap must hold F_max^T bits (F_max =
+        most free cells of any puzzle of this rank's shard); the more CTAs fit an SM next to it,
+        the better the level-synchronisation latency of one puzzle hides behind the others."""
+        if self._plan is not None:
+            return self._plan or None
+        t = self.t
+        lo, hi = shard_range(t.n_envs, self.rank, self.world)
+        blocked = t.blocked_cells()[lo:hi]
+        f_max = int(t.size * t.size - blocked.sum(1).min()) if hi > lo else 1
+        bits = max(f_max, 1) ** t.n_tiles
+        bitmap_bytes = max(16, -(-bits // 128) * 16)
+        plan = None
+        for k in ([self.want_ctas] if self.want_ctas else [8, 6, 5, 4, 3, 2, 1]):
+            budget = self.SMEM_PER_SM // k - self.STATIC_SMEM
+            if bitmap_bytes + 2048 > budget:
+                continue
+            queue = min(budget - bitmap_bytes, 64 * 1024) // 16 * 4        # entries (4 bytes each), multiple of 4
+            if self.want_queue is not None:
+                queue = max(4, min(queue, self.want_queue) // 4 * 4)
+            a = self._args(bitmap_words=bitmap_bytes // 4, queue_smem=queue, n_puzzles=0)
+            got, n_sm = C.c_int(0), C.c_int(0)
+            with torch.cuda.device(self.device):
+                rc = self.lib.ts_bfs_local_ctas_per_sm(C.byref(a), C.byref(got), C.byref(n_sm))
+            if rc == 0 and got.value >= 1:
+                grid = got.value * n_sm.value
+                spill = int(min(bits, self.MAX_SCRATCH_BYTES // 4 // grid))
+                plan = dict(bitmap_words=bitmap_bytes // 4, queue_smem=queue, grid=grid, ctas_per_sm=got.value,
+                            spill_per_cta=spill, f_max=f_max, smem_bytes=bitmap_bytes + 4 * queue)
+                break
+        self._plan = plan or {}
+        return plan
+
+    def _buf(self, name: str, n: int, dtype) -> torch.Tensor:
+        b = self._scratch.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            b = torch.empty(n, dtype=dtype, device=self.device)
+            self._scratch[name] = b
+        return b[:n]
+
+    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
+        t, dev, P = self.t, self.device, self.t.n_envs
+        plan = self.plan()
+        i32max = (1 << 31) - 1
+        states_pp = torch.zeros(P, dtype=torch.int64, device=dev)
+        depth_pp = torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev)
+        status = torch.zeros(P, dtype=torch.int32, device=dev)
+        levels = torch.zeros(self.N_LEVELS, dtype=torch.int64, device=dev)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        max_moves = 255
+        moves = torch.zeros(P, max_moves, dtype=torch.uint8, device=dev) if with_paths else None
+        lengths = torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev) if with_paths else None
+        lo, hi = shard_range(P, self.rank, self.world)
+        if plan is None:
+            status[lo:hi] = 1                                  # nothing fits on chip: everything goes to the hash-partitioned search
+        elif hi > lo:
+            ids = torch.arange(lo, hi, dtype=torch.int32, device=dev) if self.world > 1 else None
+            slab = plan["queue_smem"] + plan["spill_per_cta"]
+            a = self._args(n_puzzles=hi - lo, d_puzzle_ids=None if ids is None else ids.data_ptr(),
+                           max_depth=min(int(max_depth), i32max), bitmap_words=plan["bitmap_words"],
+                           queue_smem=plan["queue_smem"], spill_per_cta=plan["spill_per_cta"],
+                           d_spill=self._buf("spill", plan["grid"] * max(plan["spill_per_cta"], 1), torch.int32).data_ptr(),
+                           d_parent_scratch=self._buf("parents", plan["grid"] * slab, torch.int32).data_ptr() if with_paths else None,
+                           d_states_per_puzzle=states_pp.data_ptr(), d_solve_depth=depth_pp.data_ptr(),
+                           d_status=status.data_ptr(), d_levels=levels.data_ptr(), d_counters=counters.data_ptr(),
+                           d_moves=None if moves is None else moves.data_ptr(),
+                           d_lengths=None if lengths is None else lengths.data_ptr(), max_moves=max_moves)
+            with torch.cuda.device(dev):
+                check(self.lib.ts_bfs_local(C.byref(a), plan["grid"], torch.cuda.current_stream(dev).cuda_stream), "ts_bfs_local")
+        if self.world > 1:
+            dist.all_reduce(states_pp, group=self.group)
+            dist.all_reduce(depth_pp, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(levels, group=self.group)
+            dist.all_reduce(counters[1:2], group=self.group)
+            if with_paths:
+                dist.all_reduce(lengths, op=dist.ReduceOp.MAX, group=self.group)
+                dist.all_reduce(moves, op=dist.ReduceOp.MAX, group=self.group)
+        generated = int(counters[1].item())
+        lv = levels.tolist()
+        solutions = None
+        if with_paths:
+            mv, ln = moves.cpu().tolist(), lengths.cpu().tolist()
+            solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
+        # ---- puzzles that did not fit on chip: the hash-partitioned search (collective over the same ranks)
+        rest = torch.nonzero(status).flatten().tolist()
+        if rest:
+            sub = BatchedTilerSliderEnv.from_puzzles([t.puzzle(i) for i in rest], device=dev)
+            cap = self.fallback_table_capacity
+            while True:
+                try:
+                    r = BfsSolver(sub, table_capacity=cap, group=self.group).solve(
+                        max_depth=max_depth, with_paths=with_paths and self.world == 1)
+                    break
+                except RuntimeError as e:                     # visited table full: double it
+                    if "table" not in str(e) or cap >= 1 << 32:
+                        raise
+                    cap *= 2
+            idx = torch.tensor(rest, dtype=torch.int64, device=dev)
+            states_pp[idx] = r.states_per_puzzle
+            depth_pp[idx] = r.solve_depth_per_puzzle.to(torch.int32)
+            generated += r.generated
+            lv = [a_ + b_ for a_, b_ in zip(lv + [0] * max(0, len(r.levels) - len(lv)), r.levels + [0] * max(0, len(lv) - len(r.levels)))]
+            if solutions is not None and r.solutions is not None:
+                for j, i in enumerate(rest):
+                    solutions[i] = r.solutions[j]
+        while len(lv) > 1 and lv[-1] == 0:
+            lv.pop()
+        solved = depth_pp[depth_pp >= 0]
+        return BfsResult(n_states=int(sum(lv)), levels=lv, solve_depth=int(solved.min()) if solved.numel() else -1,
+                         states_per_puzzle=states_pp if per_puzzle else None,
+                         solve_depth_per_puzzle=depth_pp if per_puzzle else None,
+                         generated=generated, solutions=solutions, fallback_puzzles=len(rest))
 
 
 def solve_puzzle(puzzle: Puzzle, **kw) -> BfsResult:
