@@ -572,3 +572,49 @@ def test_argument_errors(ts):
         ts.BatchedTilerSliderEnv.from_puzzles([ts.Puzzle(3, [(0, 0)], [(0, 0)], [(1, 1)])])
     with pytest.raises(ValueError):
         ts.BatchedTilerSliderEnv.from_puzzles([ts.Puzzle(3, [], [(0, 0), (0, 0)], [(1, 1), (2, 2)])])
+
+
+@pytest.mark.parametrize("S,T,W,multi,N,seed", [(5, 1, 5, False, 1_048_576, 1001), (12, 8, 36, True, 4_194_304, 1003)])
+def test_baseline_configs_at_their_literal_sizes(ts, S, T, W, multi, N, seed):
+    """BASELINE configs 2 and 4 at their full env counts (1,048,576 / 4,194,304): the first and the
+    last 4,096 envs against the oracle over 24 steps, and size-independent properties over the
+    whole batch -- tiles stay on distinct open cells, repeating an action moves nothing, and the
+    fast path (no status byte) ends in the same state."""
+    K, n_chk = 24, 4096
+    kw = dict(seed=seed, max_steps=100, auto_reset=True, track_terminal=True)
+    env = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, **kw)
+    fast = ts.BatchedTilerSliderEnv.synthetic(N, S, T, W, multi, track_flags=False, **kw)
+    walls = env.blocked_cells()
+    g = torch.Generator(device="cuda").manual_seed(seed + 1000)
+    actions = torch.randint(0, 4, (K, env.capacity), dtype=torch.uint8, device="cuda", generator=g)
+    want = {}
+    for name, sl in (("head", slice(0, n_chk)), ("tail", slice(N - n_chk, N))):
+        blocked = walls[sl].cpu().numpy().astype(np.uint8)
+        tiles = env.positions()[sl].cpu().numpy()
+        if env.goal_mode == ts.GOAL_ORDERED:
+            targets = env.target_positions()[sl].cpu().numpy()
+        else:
+            cells = np.stack([np.flatnonzero(r) for r in env.target_positions()[sl].cpu().numpy()])
+            targets = np.stack([cells // S, cells % S], -1).astype(np.uint8)
+        want[name] = (sl, orc.rollout(S, multi, blocked, tiles, targets, actions[:, sl].cpu().numpy(), max_steps=100, auto_reset=True))
+    for k in range(K):
+        _, r, d = env.step(actions[k])
+        fast.step(actions[k])
+        for sl, w in want.values():
+            post = torch.where(d[sl][:, None, None], env.positions(env.terminal_pos[sl]), env.positions(env.pos[sl]))
+            assert np.array_equal(post.cpu().numpy(), w["pos"][k])
+            assert np.array_equal(env.flags[sl].cpu().numpy(), w["flags"][k]) and np.array_equal(r[sl].cpu().numpy(), w["reward"][k])
+    assert torch.equal(env.pos, fast.pos) and torch.equal(env.reward, fast.reward) and torch.equal(env.done, fast.done)
+    p = env.positions().to(torch.int64)
+    cell = p[..., 0] * S + p[..., 1]
+    assert int(p.max()) < S and not bool(walls.gather(1, cell).any())
+    if T > 1:
+        srt = cell.sort(dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    same = torch.full((env.capacity,), 2, dtype=torch.uint8, device="cuda")
+    env.step(same)
+    before = env.pos.clone()
+    live = ~env.done
+    env.step(same)
+    assert torch.equal(env.pos[live & ~env.done], before[live & ~env.done])
+    assert bool(((env.flags & F_INVALID) != 0)[live].all())
