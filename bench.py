@@ -332,7 +332,7 @@ class Runner:
         return out.view(self.world, -1).tolist()
 
     def measure(self, cfg: Config, n_local: int, steps: int, warmup: int, use_graph: bool = True, max_blocks: int = 30,
-                budget_s: float = 0.4, clocks: Clocks | None = None) -> dict:
+                budget_s: float = 0.4, clocks: Clocks | None = None, ramp_ms: float = RAMP_MS) -> dict:
         """Device-resident throughput of one config (see the module docstring)."""
         torch, ts = self.torch, self.ts
         env = ts.BatchedTilerSliderEnv.synthetic(n_local, cfg.size, cfg.tiles, cfg.walls, cfg.multi, seed=cfg.puzzle_seed,
@@ -363,7 +363,7 @@ class Runner:
         block()
         torch.cuda.synchronize()
         ramp_blocks, busy_ms, est_ms = 1, 0.0, None
-        while busy_ms < RAMP_MS:
+        while busy_ms < ramp_ms or est_ms is None:
             ev0.record()
             block()
             ev1.record()
@@ -559,9 +559,10 @@ def run_ours(args) -> int:
     cfg = CONFIGS[args.config]
     n_local = args.envs
     clk = Clocks(R.local)
-    head = R.measure(cfg, n_local, args.steps, args.warmup, use_graph=args.graph, clocks=clk)
+    head = R.measure(cfg, n_local, args.steps, args.warmup, use_graph=args.graph, clocks=clk, ramp_ms=args.ramp_ms,
+                     max_blocks=args.max_blocks)
     clocks = clk.summary()
-    e2e = R.e2e(cfg, n_local, max(3, min(args.steps, args.e2e_steps)))
+    e2e = R.e2e(cfg, n_local, max(3, min(args.steps, args.e2e_steps))) if args.e2e_steps > 0 else None
     line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": R.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -621,6 +622,8 @@ def main() -> int:
     ap.add_argument("--no-extra", action="store_true", help="headline config only (no `configs`, no strong-scaling figure)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every step from Python instead of replaying CUDA graphs")
+    ap.add_argument("--ramp-ms", type=float, default=RAMP_MS, help="GPU-busy time before the timed blocks (profiling runs: 0)")
+    ap.add_argument("--max-blocks", type=int, default=30, help="upper bound on the timed blocks (profiling runs: 5)")
     ap.add_argument("--bfs-puzzles", type=int, default=65_536, help="c5: puzzles per GPU")
     ap.add_argument("--bfs-check", type=int, default=1024, help="c5: puzzles cross-checked against the CPU oracle's BFS")
     args = ap.parse_args()
