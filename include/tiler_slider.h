@@ -315,12 +315,14 @@ int ts_bfs_levels(const ts_bfs_args *a, int32_t first_depth, int32_t n_levels, u
  * K6 ts_bfs_local: breadth-first search of many small puzzles, one CTA per puzzle, on chip
  * (csrc/ts_bfs_local.cu).  Same successor function, goal test, canonical states and result
  * definitions as the hash-partitioned search above; boards of size <= 8 with 1..4 tiles.
- * The visited set of a puzzle is a bitmap in shared memory over the perfect hash
- * state -> sum(rank(tile i) * F^i), F = free cells of the puzzle, rank = index of a cell among
- * them; the frontier queue holds `queue_smem` states in shared memory and spills to
- * d_spill[cta][spill_per_cta].  Persistent grid: CTAs draw puzzles from the ticket counter.
+ * The visited set of a puzzle is a bitmap in shared memory over a perfect hash of the state (the
+ * arrangement number of its T tiles among the F free cells of the puzzle: F!/(F-T)! bits,
+ * bitmap_words u32 words, a multiple of 4); the frontier queue is a ring of `queue_smem` states
+ * (a power of two >= 32) in shared memory -- the level being expanded and the one being appended --
+ * and spills to d_spill[cta][spill_per_cta], indexed by discovery order.  Persistent grid: CTAs
+ * draw puzzles from the ticket counter.
  *   d_puzzle_ids       optional: search puzzles d_puzzle_ids[0 .. n_puzzles) instead of 0 .. n_puzzles-1
- *   d_status[pid]      0 searched; 1 F^T bits exceed bitmap_words*32; 2 spill slab exhausted; 3 deeper
+ *   d_status[pid]      0 searched; 1 state space exceeds bitmap_words*32 bits; 2 spill slab exhausted; 3 deeper
  *                      than 255 levels -- for != 0 nothing else of the puzzle is valid (search it
  *                      with the hash-partitioned path)
  *   d_states_per_puzzle[pid], d_solve_depth[pid] (-1: no goal within max_depth)
@@ -328,7 +330,7 @@ int ts_bfs_levels(const ts_bfs_args *a, int32_t first_depth, int32_t n_levels, u
  *   d_counters         [0] ticket (zero on entry), [1] += successors generated, [3] = max(depth reached)
  *   d_lengths / d_moves / d_parent_scratch  optional shortest move string per puzzle (0..3, root
  *                      first; length -1: unsolved or longer than max_moves); d_parent_scratch holds
- *                      grid * (queue_smem + spill_per_cta) words
+ *                      grid * spill_per_cta words (spill_per_cta then bounds the states of a puzzle)
  * ts_bfs_local_smem_bytes: dynamic shared memory of a launch with these arguments;
  * ts_bfs_local_ctas_per_sm: resident CTAs per SM and the SM count, to size the grid.
  * ------------------------------------------------------------------------------------- */

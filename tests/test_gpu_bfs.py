@@ -251,9 +251,9 @@ def test_local_bfs_agrees_with_hash_partitioned_search(ts):
 
 def test_local_bfs_queue_spill_and_fallback(ts):
     """With only 64 queue entries in shared memory nearly every state of every puzzle goes through
-    the HBM spill slab (paths included).  With two walls the state space (34^4 bits = 167 KB) does
-    not fit the bitmap of two CTAs per SM: the planner drops to one CTA per SM; asked for more than
-    fit, the puzzles are searched by the hash-partitioned path instead (fallback), same answers."""
+    the HBM spill slab (paths included).  With two walls the state space (34*33*32*31 bits = 139 KB)
+    does not fit the bitmap of two CTAs per SM: the planner drops to one CTA per SM; asked for more
+    than fit, the puzzles are searched by the hash-partitioned path instead (fallback), same answers."""
     from tiler_slider_b200.bfs import BfsSolver, LocalBfs
     batch = ts.BatchedTilerSliderEnv.synthetic(300, 6, 4, 8, True, seed=5)
     ref = BfsSolver(batch, table_capacity=1 << 22).solve(with_paths=True)
@@ -268,7 +268,7 @@ def test_local_bfs_queue_spill_and_fallback(ts):
         if res.solutions[e] is not None:
             bl = [(c // 6, c % 6) for c in np.flatnonzero(blocked[e])]
             assert _replay((6, bl, tiles[e].tolist(), targets[e].tolist(), True), res.solutions[e])[:1] == [len(res.solutions[e])]
-    few_walls = ts.BatchedTilerSliderEnv.synthetic(64, 6, 4, 2, True, seed=9)      # F = 34: 34^4 bits = 167 KB
+    few_walls = ts.BatchedTilerSliderEnv.synthetic(64, 6, 4, 2, True, seed=9)      # F = 34: 139 KB of bitmap
     want = BfsSolver(few_walls, table_capacity=1 << 25).solve()
     one = LocalBfs(few_walls)
     got = one.solve()

@@ -616,23 +616,25 @@ class LocalBfs:
         lo, hi = shard_range(t.n_envs, self.rank, self.world)
         blocked = t.blocked_cells()[lo:hi]
         f_max = int(t.size * t.size - blocked.sum(1).min()) if hi > lo else 1
-        bits = max(f_max, 1) ** t.n_tiles
+        bits = 1
+        for i in range(t.n_tiles):                               # arrangements of T distinct tiles on F_max cells
+            bits *= max(f_max - i, 1)
         bitmap_bytes = max(16, -(-bits // 128) * 16)
         plan = None
         for k in ([self.want_ctas] if self.want_ctas else [8, 6, 5, 4, 3, 2, 1]):
             budget = self.SMEM_PER_SM // k - self.STATIC_SMEM
-            if bitmap_bytes + 2048 > budget:
+            if bitmap_bytes + 1024 > budget:
                 continue
-            queue = min(budget - bitmap_bytes, 64 * 1024) // 16 * 4        # entries (4 bytes each), multiple of 4
+            queue = 1 << (min(budget - bitmap_bytes, 64 * 1024) // 4).bit_length() - 1     # ring entries: a power of two
             if self.want_queue is not None:
-                queue = max(4, min(queue, self.want_queue) // 4 * 4)
+                queue = max(32, 1 << (min(queue, self.want_queue).bit_length() - 1))
             a = self._args(bitmap_words=bitmap_bytes // 4, queue_smem=queue, n_puzzles=0)
             got, n_sm = C.c_int(0), C.c_int(0)
             with torch.cuda.device(self.device):
                 rc = self.lib.ts_bfs_local_ctas_per_sm(C.byref(a), C.byref(got), C.byref(n_sm))
             if rc == 0 and got.value >= 1:
                 grid = got.value * n_sm.value
-                spill = int(min(bits, self.MAX_SCRATCH_BYTES // 4 // grid))
+                spill = int(min(bits + 1, self.MAX_SCRATCH_BYTES // 4 // grid))
                 plan = dict(bitmap_words=bitmap_bytes // 4, queue_smem=queue, grid=grid, ctas_per_sm=got.value,
                             spill_per_cta=spill, f_max=f_max, smem_bytes=bitmap_bytes + 4 * queue)
                 break
@@ -663,7 +665,7 @@ class LocalBfs:
             status[lo:hi] = 1                                  # nothing fits on chip: everything goes to the hash-partitioned search
         elif hi > lo:
             ids = torch.arange(lo, hi, dtype=torch.int32, device=dev) if self.world > 1 else None
-            slab = plan["queue_smem"] + plan["spill_per_cta"]
+            slab = plan["spill_per_cta"]
             a = self._args(n_puzzles=hi - lo, d_puzzle_ids=None if ids is None else ids.data_ptr(),
                            max_depth=min(int(max_depth), i32max), bitmap_words=plan["bitmap_words"],
                            queue_smem=plan["queue_smem"], spill_per_cta=plan["spill_per_cta"],

@@ -7,12 +7,14 @@
 // per successor, 9 % of the HBM roofline.  Here the visited set of a puzzle never leaves the SM:
 //   * it is a BITMAP over a perfect hash of the state: a tile can only stand on one of the F free
 //     cells of ITS puzzle, so state -> sum(rank(tile i) * F^i) with rank = index of the cell
-//     among the free cells is collision free, and F^T bits fit shared memory (28^4 bits = 77 KB for
-//     the benchmark shape; 5.7 KB for the reference's real levels).  Dedup = one shared-memory
-//     atomicOr per successor, no probing, no table overflow;
-//   * the frontier is an append-only queue of 32-bit states in discovery order (= BFS order): its
-//     first entries live in shared memory, the rest spills to a per-CTA slab in HBM with purely
-//     sequential traffic; level boundaries are two indices;
+//     among the free cells NOT TAKEN BY TILES 0..i-1 (mixed radix F, F-1, ...) is collision free, and
+//     F!/(F-T)! bits fit shared memory (28*27*26*25 bits = 60 KB for the benchmark shape, three CTAs
+//     per SM; 5 KB for the reference's real levels).  Dedup = one shared-memory atomicOr per
+//     successor, no probing, no table overflow;
+//   * the frontier is an append-only queue of 32-bit states in discovery order (= BFS order); the
+//     level being expanded and the one being appended live in a shared-memory ring, whatever
+//     exceeds it spills to a per-CTA slab in HBM with purely sequential traffic; level boundaries
+//     are two indices;
 //   * persistent CTAs draw puzzles from a ticket counter (puzzle sizes vary 100x).
 // Thread = one (state, move) pair, so a level of n states offers 4n-way parallelism; new states
 // are appended with one shared-memory atomic per warp; one __syncthreads per level (three rotating
@@ -75,10 +77,15 @@ __global__ void __launch_bounds__(LOCAL_THREADS) bfs_local_kernel(const ts_bfs_l
     __shared__ long long s_ticket;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t QS = (uint32_t)a.queue_smem;
+    // The queue's shared-memory part is a RING over discovery indices (queue_smem = R, a power of two):
+    // BFS only ever reads the level being expanded and appends the next one, so an entry p is kept
+    // in ring[p % R] when it is appended within R of the start of the level being expanded (lo), and
+    // in the HBM slab spill[p] otherwise; one level later the reader applies the same test with that
+    // level's lo (prev_lo).  An append to slot p % R overwrites entry p - R < lo: consumed long ago.
+    const uint32_t R = (uint32_t)a.queue_smem, RMASK = R - 1u;
     uint32_t* const spill = a.d_spill + (size_t)blockIdx.x * (size_t)a.spill_per_cta;
-    uint32_t* const parents = a.d_parent_scratch ? a.d_parent_scratch + (size_t)blockIdx.x * (size_t)(QS + a.spill_per_cta) : nullptr;
-    const uint32_t q_cap = QS + (uint32_t)a.spill_per_cta;
+    uint32_t* const parents = a.d_parent_scratch ? a.d_parent_scratch + (size_t)blockIdx.x * (size_t)a.spill_per_cta : nullptr;
+    const uint32_t q_cap = (uint32_t)a.spill_per_cta;       // discovery indices the slabs can address
     for (uint32_t k = tid; k < LOCAL_HIST; k += LOCAL_THREADS) hist[k] = 0;
     unsigned long long generated = 0;            // thread 0: successors generated by completed puzzles
     uint32_t deepest = 0;
@@ -106,11 +113,12 @@ __global__ void __launch_bounds__(LOCAL_THREADS) bfs_local_kernel(const ts_bfs_l
             const uint32_t bit = pos_to_bit<S>(tid);
             lut[tid] = bit < 64 ? (uint8_t)__popcll(free_cells & ((1ull << bit) - 1ull)) : 0;
         }
+        // states = arrangements of T distinct tiles on F cells: F (F-1) ... (F-T+1) bits
         unsigned long long bits = 1;
 #pragma unroll
-        for (int t = 0; t < T; ++t) bits *= F;
+        for (int t = 0; t < T; ++t) bits *= (F > (uint32_t)t ? F - (uint32_t)t : 1u);
         const uint32_t words = (uint32_t)((bits + 31) / 32);
-        if (words > (uint32_t)a.bitmap_words || q_cap < 1) {     // does not fit this launch: left to the hash-partitioned search
+        if (words > (uint32_t)a.bitmap_words) {     // does not fit this launch: left to the hash-partitioned search
             if (tid == 0) a.d_status[pid] = 1;
             continue;
         }
@@ -118,23 +126,33 @@ __global__ void __launch_bounds__(LOCAL_THREADS) bfs_local_kernel(const ts_bfs_l
         if (tid == 0) { cnt[0] = cnt[1] = cnt[2] = 0; s_solve = 0xFFFFFFFFu; s_over = 0; s_goal = ~0ull; }
         __syncthreads();
 
+        // perfect hash of a state: its tiles stand on DISTINCT free cells, so digit i = rank of tile i
+        // among the cells not taken by tiles 0..i-1, mixed radix F, F-1, ... (28^4 bits would not leave
+        // room for three CTAs per SM, 28*27*26*25 bits do)
         auto state_index = [&](uint32_t q) {
+            uint32_t r[T];
+            static_for<0, T>([&](auto I) { constexpr int i = decltype(I)::value; r[i] = lut[byte_of<i>(q)]; });
             uint32_t idx = 0;
-            static_for<0, T>([&](auto I) { constexpr int i = decltype(I)::value; idx = idx * F + lut[byte_of<i>(q)]; });
+            static_for<0, T>([&](auto I) {
+                constexpr int i = T - 1 - decltype(I)::value;          // most significant digit first
+                uint32_t d = r[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) d -= (r[j] < r[i]) ? 1u : 0u;
+                idx = idx * (F - (uint32_t)i) + d;
+            });
             return idx;
         };
-        auto q_get = [&](uint32_t i) { return i < QS ? queue[i] : spill[i - QS]; };
 
         if (tid == 0) {
             const uint32_t idx = state_index(q_init);
             bitmap[idx >> 5] |= 1u << (idx & 31u);
-            if (QS) queue[0] = q_init; else spill[0] = q_init;
+            queue[0] = q_init;
             if (parents) parents[0] = 0xFFFFFFFFu;
             plevel[0] = 1;
         }
         __syncthreads();
 
-        uint32_t lo = 0, hi = 1, depth = 0;
+        uint32_t lo = 0, hi = 1, depth = 0, prev_lo = 0;
         unsigned long long gen_p = 0;
         bool too_deep = false;
         while (lo < hi && depth < (uint32_t)a.max_depth) {
@@ -149,7 +167,7 @@ __global__ void __launch_bounds__(LOCAL_THREADS) bfs_local_kernel(const ts_bfs_l
                 bool is_new = false;
                 uint32_t qn = 0;
                 if (live) {
-                    const uint32_t q0 = q_get(src);
+                    const uint32_t q0 = (src - prev_lo) < R ? queue[src & RMASK] : spill[src];
                     uint32_t q[1] = {q0};
                     slide_env<S, T>(q, walls, d >> 1, (d & 1u) ^ 1u);
                     bool won = a.never_win == 0;
@@ -177,16 +195,20 @@ __global__ void __launch_bounds__(LOCAL_THREADS) bfs_local_kernel(const ts_bfs_l
                     pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(m) - 1);
                     if (is_new) {
                         pos += hi + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                        if (pos < QS) queue[pos] = qn;
-                        else if (pos < q_cap) spill[pos - QS] = qn;
+                        if (pos - lo < R) queue[pos & RMASK] = qn;
+                        else if (pos < q_cap) spill[pos] = qn;
                         else s_over = 1;
-                        if (parents && pos < q_cap) parents[pos] = (src << 2) | d;
+                        if (parents) {
+                            if (pos < q_cap) parents[pos] = (src << 2) | d;
+                            else s_over = 1;
+                        }
                     }
                 }
             }
             __syncthreads();
             const uint32_t n_new = *my_cnt;
             gen_p += 4ull * (hi - lo);
+            prev_lo = lo;
             lo = hi;
             hi += n_new;
             ++depth;
@@ -283,7 +305,8 @@ static int local_check(const ts_bfs_local_args* a) {
     if (a->size < 1 || a->size > 8) return TS_E_UNSUPPORTED;
     if (a->n_tiles < 1 || a->n_tiles > 4) return TS_E_UNSUPPORTED;            // 32-bit states
     if (a->goal_mode != TS_GOAL_ORDERED && a->goal_mode != TS_GOAL_SET) return TS_E_BAD_ARGUMENT;
-    if (a->bitmap_words < 4 || a->bitmap_words % 4 || a->queue_smem < 0 || a->spill_per_cta < 0) return TS_E_BAD_ARGUMENT;
+    if (a->bitmap_words < 4 || a->bitmap_words % 4 || a->queue_smem < 32 || (a->queue_smem & (a->queue_smem - 1)) || a->spill_per_cta < 0)
+        return TS_E_BAD_ARGUMENT;      // the shared-memory queue is a power-of-two ring
     return 0;
 }
 
