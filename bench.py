@@ -555,6 +555,11 @@ def ncu_traffic(cfg: Config, n_local: int) -> dict | None:
 
 
 def run_ours(args) -> int:
+    # stdout carries exactly ONE line, the JSON: libraries that print to fd 1 (NCCL's version banner
+    # when a communicator is created) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     R = Runner()
     cfg = CONFIGS[args.config]
     n_local = args.envs
@@ -601,7 +606,7 @@ def run_ours(args) -> int:
                                         "sample": f"{n_cpu} envs x 300 steps of the same workload, single process, "
                                                   "oracle/py_port.py (reference Python step loop restated)",
                                         "c_oracle_env_steps_per_s_1core": c_oracle_rate(cfg)}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     R.barrier()
     R.close()
     return 0

@@ -1,12 +1,15 @@
 """bfs_bench.py -- BASELINE config 5: batched breadth-first search with hash-partitioned dedup.
 
-    python bfs_bench.py [--puzzles P] [--check C]
+    python bfs_bench.py [--puzzles P] [--check C] [--mode hash|local]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bfs_bench.py --puzzles P
 
 P synthetic 6x6 puzzles with 4 coloured tiles and 8 walls (K0, the create_simple_env recipe) are
-searched to exhaustion at once; key = puzzle id || positions.  With N ranks every rank owns the
-keys that hash to it and one NCCL all-to-all per depth moves the successors to their owners
-(tiler_slider_b200/bfs.py).  Work unit: one generated successor (state x move), SURVEY 8(d).
+searched to exhaustion at once.  --mode hash: key = puzzle id || positions, one visited table in
+HBM; with N ranks every rank owns the keys that hash to it and the successors travel to their
+owners once per depth (NCCL all-to-all, or the expand kernel writing into peer inboxes over NVLink).
+--mode local: one CTA per puzzle with the visited set in shared memory (K6); with N ranks the
+puzzles are sharded by index and nothing is exchanged (tiler_slider_b200/bfs.py).  Work unit: one
+generated successor (state x move), SURVEY 8(d).
 The first C puzzles are cross-checked against the CPU oracle's BFS (state count, solve depth).
 Prints one JSON line on rank 0.
 """
@@ -33,6 +36,8 @@ def main() -> int:
     ap.add_argument("--check", type=int, default=8, help="puzzles cross-checked against the CPU oracle on rank 0")
     ap.add_argument("--exchange", choices=["auto", "nccl", "p2p"], default="auto",
                     help="multi-GPU: NCCL all-to-all, or the expand kernel writing into peer inboxes over NVLink")
+    ap.add_argument("--mode", choices=["hash", "local"], default="hash",
+                    help="hash: one visited table in HBM, hash-partitioned over the ranks; local: one CTA per puzzle, on chip (K6)")
     ap.add_argument("--profile", action="store_true", help="a third, phase-synchronised search: wall time per phase (rank 0)")
     args = ap.parse_args()
 
@@ -40,7 +45,7 @@ def main() -> int:
     import torch
     import torch.distributed as dist
     import tiler_slider_b200 as ts
-    from tiler_slider_b200.bfs import BfsSolver
+    from tiler_slider_b200.bfs import BfsSolver, LocalBfs
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -49,7 +54,7 @@ def main() -> int:
         dist.init_process_group("nccl", device_id=dev)
     table = ts.BatchedTilerSliderEnv.synthetic(args.puzzles, args.size, args.tiles, args.walls, True, seed=args.seed, device=dev)
     log2 = args.table_log2 or max(16, int(np.ceil(np.log2(args.puzzles * 16384 / world))))   # ~3,400 states per puzzle on average
-    solver = BfsSolver(table, table_capacity=1 << log2, exchange=args.exchange)
+    solver = BfsSolver(table, table_capacity=1 << log2, exchange=args.exchange) if args.mode == "hash" else LocalBfs(table)
     if world > 1:   # create the NCCL communicator and its all-to-all channels outside the timed region
         w = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_to_all_single(torch.empty_like(w), w)
@@ -69,7 +74,7 @@ def main() -> int:
         times.append(time.perf_counter() - t0)
     dt_cold, dt = times
     phases = None
-    if args.profile:
+    if args.profile and args.mode == "hash":
         solver.profile = True
         solver.solve()
         phases = {k: round(v, 4) for k, v in solver.phase_seconds.items()}
@@ -88,7 +93,9 @@ def main() -> int:
     if rank == 0:
         solved = int((res.solve_depth_per_puzzle >= 0).sum())
         print(json.dumps({"config": f"BFS {args.puzzles} puzzles {args.size}x{args.size}/{args.tiles} tiles/{args.walls} walls, "
-                                    f"{world} GPU(s), table 2^{log2} per rank, exchange {solver.exchange if world > 1 else 'none'}",
+                                    f"{world} GPU(s), " + (f"table 2^{log2} per rank, exchange {solver.exchange if world > 1 else 'none'}"
+                                                           if args.mode == "hash" else f"one CTA per puzzle on chip, plan {solver.plan()}"),
+                          "mode": args.mode,
                           "n_gpus": world, "unique_states": res.n_states, "generated_successors": res.generated,
                           "depth": len(res.levels) - 1, "seconds": dt, "seconds_cold": dt_cold,
                           "generated_successors_per_s": res.generated / dt, "unique_states_per_s": res.n_states / dt,

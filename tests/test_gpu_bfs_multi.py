@@ -14,8 +14,8 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
 
 
-def _bench(world: int, exchange: str, puzzles: int = 4096) -> dict:
-    cmd = [sys.executable, "bfs_bench.py", "--puzzles", str(puzzles), "--check", "16", "--exchange", exchange]
+def _bench(world: int, exchange: str, puzzles: int = 4096, mode: str = "hash") -> dict:
+    cmd = [sys.executable, "bfs_bench.py", "--puzzles", str(puzzles), "--check", "64", "--exchange", exchange, "--mode", mode]
     if world > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", "29541"] + cmd[1:]
@@ -32,3 +32,8 @@ def test_two_gpu_exchanges_match_single_gpu():
         assert two["oracle_check"]["ok"]
         for key in ("unique_states", "generated_successors", "depth", "puzzles_solved", "max_solve_depth"):
             assert two[key] == one[key], (exchange, key)
+    # the on-chip search, puzzles sharded over two ranks with no exchange: same totals again
+    local = _bench(2, "nccl", mode="local")
+    assert local["oracle_check"]["ok"] and local["mode"] == "local"
+    for key in ("unique_states", "generated_successors", "depth", "puzzles_solved", "max_solve_depth"):
+        assert local[key] == one[key], ("local", key)
