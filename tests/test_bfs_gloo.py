@@ -163,3 +163,116 @@ def _shard_worker(rank, world, port, q):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     q.put((rank, lo, hi, float(t.item())))
     dist.destroy_process_group()
+
+
+# ---- LocalBfs (K6 driver): puzzles sharded over the ranks, no exchange, results merged once ------------
+class OracleLocalKernels:
+    """Same interface as CudaLocalKernels (plan / search / puzzle), on CPU tensors: a plain BFS over
+    the oracle's move per puzzle.  `too_big` puzzles report status 1 like a puzzle whose state space
+    does not fit the shared-memory bitmap."""
+    N_LEVELS, MAX_MOVES = 256, 255
+
+    def __init__(self, puzzles, too_big=()):
+        from oracle import oracle as orc
+        self.device, self.puzzles, self.too_big, self.orc = torch.device("cpu"), puzzles, set(too_big), orc
+
+    def plan(self, lo, hi):
+        return {"ctas_per_sm": 1, "queue_smem": 64}
+
+    def search(self, lo, hi, max_depth, out):
+        for pid in range(lo, hi):
+            if pid in self.too_big:
+                out["status"][pid] = 1
+                continue
+            p = self.puzzles[pid]
+            st = self.orc.OracleState(p["size"], p["blocked"], p["tiles"], p["targets"], p["multi_color"])
+            S = st.size
+
+            def key(locs):
+                cells = [r * S + c for r, c in locs]
+                return tuple(cells if st.multi_color else sorted(cells))
+            start = key(st.current_locations)
+            seen, frontier, depth, solve, goal = {start: None}, [start], 0, -1, None
+            out["levels"][0] += 1
+            while frontier and depth < max_depth:
+                nxt = []
+                for k in frontier:
+                    for d in range(4):
+                        st.set_locations([(c // S, c % S) for c in k])
+                        won = st.move(d)
+                        k2 = key(st.current_locations)
+                        if won and solve < 0:
+                            solve, goal = depth + 1, (k, d)
+                        if k2 not in seen:
+                            seen[k2] = (k, d)
+                            nxt.append(k2)
+                out["counters"][1] += 4 * len(frontier)
+                depth += 1
+                if nxt:
+                    out["levels"][depth] += len(nxt)
+                frontier = nxt
+            out["states"][pid], out["depth"][pid] = len(seen), solve
+            if out.get("lengths") is not None:
+                moves = []
+                link = goal
+                while link is not None:
+                    moves.append(link[1])
+                    link = seen[link[0]]
+                out["lengths"][pid] = len(moves) if goal is not None else -1
+                for i, m in enumerate(reversed(moves)):
+                    out["moves"][pid, i] = m
+
+
+def _local_worker(rank, world, port, puzzles, too_big, kw, q):
+    sys.path.insert(0, ROOT)
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tiler_slider_b200.bfs import BfsSolver, LocalBfs
+
+    def fallback(rest, max_depth, with_paths):          # the hash-partitioned driver on stand-in kernels, collective over the same ranks
+        return BfsSolver(kernels=OracleBfsKernels([puzzles[i] for i in rest]), n_puzzles=len(rest), table_capacity=1 << 16).solve(max_depth=max_depth)
+    res = LocalBfs(kernels=OracleLocalKernels(puzzles, too_big), n_puzzles=len(puzzles), fallback=fallback).solve(**kw)
+    if rank == 0:
+        q.put((res.n_states, res.levels, res.solve_depth, res.states_per_puzzle.tolist(), res.solve_depth_per_puzzle.tolist(),
+               res.generated, res.solutions, res.fallback_puzzles))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_local(world, puzzles, too_big=(), port=29535, **kw):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_local_worker, args=(r, world, port, puzzles, tuple(too_big), kw, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got
+
+
+def test_local_bfs_driver_shards_puzzles_over_gloo():
+    """K6's driver on two gloo ranks: five puzzles sharded 3 + 2, nothing exchanged during the
+    search, per-puzzle results / level histogram / successor count / shortest solutions merged at
+    the end -- equal to the one-rank run and to the known answers; then with one puzzle reported as
+    not fitting on chip, which both ranks hand to the hash-partitioned driver together."""
+    gold = {b["name"]: b for b in _golden_bfs()}
+    names = ["puzzle_multi_111", "puzzle_multi_180", "puzzle_multi_111", "puzzle_multi_180", "puzzle_multi_111"]
+    batch = [gold[n] for n in names]
+    want_states = [gold[n]["n_states"] for n in names]
+    want_depth = [gold[n]["solve_depth"] for n in names]
+    want_levels = [sum(gold[n]["levels"][i] if i < len(gold[n]["levels"]) else 0 for n in names) for i in range(25)]
+    one = _run_local(1, batch, with_paths=True)
+    two = _run_local(2, batch, with_paths=True, port=29536)
+    for got in (one, two):
+        n_states, levels, solve_depth, spp, dpp, generated, solutions, n_fb = got
+        assert spp == want_states and dpp == want_depth and n_fb == 0
+        assert levels == want_levels and n_states == sum(want_states) and solve_depth == 8 and generated == 4 * n_states
+        assert [len(s) for s in solutions] == want_depth
+    assert one[:6] == two[:6]
+    fb = _run_local(2, batch, too_big=[1, 4], port=29537)
+    assert fb[3] == want_states and fb[4] == want_depth and fb[1] == want_levels and fb[7] == 2 and fb[5] == 4 * sum(want_states)
+    lim = _run_local(2, batch, max_depth=5, port=29538)
+    assert lim[1] == want_levels[:6] and lim[4] == [-1] * 5

@@ -568,34 +568,23 @@ class BfsSolver:
                          solve_depth_per_puzzle=depth_pp, generated=generated, solutions=solutions)
 
 
-class LocalBfs:
-    """Batched BFS with one CTA per puzzle and the visited set in shared memory (K6,
-    csrc/ts_bfs_local.cu): for batches of small puzzles, which is what the domain offers (a 6x6
-    board with 4 tiles and 8 walls has 3,300 reachable states on average, the reference's real
-    levels 51-950).  Several ranks: the puzzles are sharded by index (`shard_range`), every rank
-    searches its shard with no exchange at all, and the per-puzzle results are combined once at
-    the end.  A puzzle that does not fit on chip (state space above the shared-memory bitmap,
-    more than 255 levels) is searched by the hash-partitioned `BfsSolver` instead.  Same result
-    definitions as BfsSolver; boards of size <= 8 with 1..4 tiles."""
+class CudaLocalKernels:
+    """ctypes front-end of ts_bfs_local for one puzzle table: the shared-memory plan and the launch
+    that searches a contiguous range of puzzles into caller-provided result tensors."""
 
     N_LEVELS = 256
     SMEM_PER_SM = 228 * 1024
     STATIC_SMEM = 4 * 1024          # the kernel's static shared memory + the per-CTA reservation
     MAX_SCRATCH_BYTES = 4 << 30
+    MAX_MOVES = 255
 
-    def __init__(self, puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv, *, device="cuda", group=None,
-                 ctas_per_sm: int | None = None, queue_smem: int | None = None, fallback_table_capacity: int = 1 << 24):
-        table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else \
-            BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
+    def __init__(self, table: BatchedTilerSliderEnv, ctas_per_sm: int | None = None, queue_smem: int | None = None):
         if table.size > 8 or not 1 <= table.n_tiles <= 4:
             raise ValueError("the on-chip BFS covers board sizes up to 8 with 1 to 4 tiles")
-        self.t, self.lib, self.device, self.group = table, lib(), table.device, group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.t, self.lib, self.device = table, lib(), table.device
         self.want_ctas = ctas_per_sm
-        self.want_queue = queue_smem        # cap on the queue entries kept in shared memory (tests: force the spill path)
-        self.fallback_table_capacity = fallback_table_capacity
-        self._plan = None
+        self.want_queue = queue_smem        # cap on the ring entries kept in shared memory (tests: force the spill path)
+        self._plans: dict[tuple[int, int], dict] = {}
         self._scratch: dict[str, torch.Tensor] = {}
 
     def _args(self, **kw) -> BfsLocalArgs:
@@ -606,14 +595,13 @@ class LocalBfs:
         base.update(kw)
         return BfsLocalArgs(**base)
 
-    def plan(self) -> dict | None:
-        """Shared-memory split and grid of the launch: the bitmap must hold F_max^T bits (F_max =
-        most free cells of any puzzle of this rank's shard); the more CTAs fit an SM next to it,
-        the better the level-synchronisation latency of one puzzle hides behind the others."""
-        if self._plan is not None:
-            return self._plan or None
+    def plan(self, lo: int, hi: int) -> dict | None:
+        """Shared-memory split and grid for puzzles [lo, hi): the bitmap must hold F!/(F-T)! bits for
+        F = the most free cells of any of them; the more CTAs fit an SM next to it, the better the
+        level-synchronisation latency of one puzzle hides behind the others."""
+        if (lo, hi) in self._plans:
+            return self._plans[(lo, hi)] or None
         t = self.t
-        lo, hi = shard_range(t.n_envs, self.rank, self.world)
         blocked = t.blocked_cells()[lo:hi]
         f_max = int(t.size * t.size - blocked.sum(1).min()) if hi > lo else 1
         bits = 1
@@ -638,7 +626,7 @@ class LocalBfs:
                 plan = dict(bitmap_words=bitmap_bytes // 4, queue_smem=queue, grid=grid, ctas_per_sm=got.value,
                             spill_per_cta=spill, f_max=f_max, smem_bytes=bitmap_bytes + 4 * queue)
                 break
-        self._plan = plan or {}
+        self._plans[(lo, hi)] = plan or {}
         return plan
 
     def _buf(self, name: str, n: int, dtype) -> torch.Tensor:
@@ -648,69 +636,121 @@ class LocalBfs:
             self._scratch[name] = b
         return b[:n]
 
-    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
-        t, dev, P = self.t, self.device, self.t.n_envs
-        plan = self.plan()
-        i32max = (1 << 31) - 1
-        states_pp = torch.zeros(P, dtype=torch.int64, device=dev)
-        depth_pp = torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev)
-        status = torch.zeros(P, dtype=torch.int32, device=dev)
-        levels = torch.zeros(self.N_LEVELS, dtype=torch.int64, device=dev)
-        counters = torch.zeros(8, dtype=torch.int64, device=dev)
-        max_moves = 255
-        moves = torch.zeros(P, max_moves, dtype=torch.uint8, device=dev) if with_paths else None
-        lengths = torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev) if with_paths else None
-        lo, hi = shard_range(P, self.rank, self.world)
+    def puzzle(self, i: int) -> Puzzle:
+        return self.t.puzzle(i)
+
+    def search(self, lo: int, hi: int, max_depth: int, out: dict) -> None:
+        """Search puzzles [lo, hi) into out = {states, depth, status, levels, counters[, moves, lengths]}
+        (tensors over ALL puzzles of the table); puzzles that do not fit get status != 0."""
+        plan = self.plan(lo, hi)
         if plan is None:
-            status[lo:hi] = 1                                  # nothing fits on chip: everything goes to the hash-partitioned search
-        elif hi > lo:
-            ids = torch.arange(lo, hi, dtype=torch.int32, device=dev) if self.world > 1 else None
-            slab = plan["spill_per_cta"]
-            a = self._args(n_puzzles=hi - lo, d_puzzle_ids=None if ids is None else ids.data_ptr(),
-                           max_depth=min(int(max_depth), i32max), bitmap_words=plan["bitmap_words"],
-                           queue_smem=plan["queue_smem"], spill_per_cta=plan["spill_per_cta"],
-                           d_spill=self._buf("spill", plan["grid"] * max(plan["spill_per_cta"], 1), torch.int32).data_ptr(),
-                           d_parent_scratch=self._buf("parents", plan["grid"] * slab, torch.int32).data_ptr() if with_paths else None,
-                           d_states_per_puzzle=states_pp.data_ptr(), d_solve_depth=depth_pp.data_ptr(),
-                           d_status=status.data_ptr(), d_levels=levels.data_ptr(), d_counters=counters.data_ptr(),
-                           d_moves=None if moves is None else moves.data_ptr(),
-                           d_lengths=None if lengths is None else lengths.data_ptr(), max_moves=max_moves)
-            with torch.cuda.device(dev):
-                check(self.lib.ts_bfs_local(C.byref(a), plan["grid"], torch.cuda.current_stream(dev).cuda_stream), "ts_bfs_local")
-        if self.world > 1:
+            out["status"][lo:hi] = 1                           # nothing fits on chip
+            return
+        if hi <= lo:
+            return
+        dev = self.device
+        ids = torch.arange(lo, hi, dtype=torch.int32, device=dev) if lo else None
+        with_paths = out.get("lengths") is not None
+        a = self._args(n_puzzles=hi - lo, d_puzzle_ids=None if ids is None else ids.data_ptr(),
+                       max_depth=min(int(max_depth), (1 << 31) - 1), bitmap_words=plan["bitmap_words"],
+                       queue_smem=plan["queue_smem"], spill_per_cta=plan["spill_per_cta"],
+                       d_spill=self._buf("spill", plan["grid"] * max(plan["spill_per_cta"], 1), torch.int32).data_ptr(),
+                       d_parent_scratch=self._buf("parents", plan["grid"] * plan["spill_per_cta"], torch.int32).data_ptr() if with_paths else None,
+                       d_states_per_puzzle=out["states"].data_ptr(), d_solve_depth=out["depth"].data_ptr(),
+                       d_status=out["status"].data_ptr(), d_levels=out["levels"].data_ptr(), d_counters=out["counters"].data_ptr(),
+                       d_moves=out["moves"].data_ptr() if with_paths else None,
+                       d_lengths=out["lengths"].data_ptr() if with_paths else None, max_moves=self.MAX_MOVES)
+        with torch.cuda.device(dev):
+            check(self.lib.ts_bfs_local(C.byref(a), plan["grid"], torch.cuda.current_stream(dev).cuda_stream), "ts_bfs_local")
+
+
+class LocalBfs:
+    """Batched BFS with one CTA per puzzle and the visited set in shared memory (K6,
+    csrc/ts_bfs_local.cu): for batches of small puzzles, which is what the domain offers (a 6x6
+    board with 4 tiles and 8 walls has 3,300 reachable states on average, the reference's real
+    levels 51-950).  Several ranks: the puzzles are sharded by index (`shard_range`), every rank
+    searches its shard with no exchange at all, and the per-puzzle results are combined once at
+    the end.  A puzzle that does not fit on chip (state space above the shared-memory bitmap,
+    more than 255 levels) is searched by the hash-partitioned `BfsSolver` instead.  Same result
+    definitions as BfsSolver; boards of size <= 8 with 1..4 tiles.
+
+    The device work sits behind `CudaLocalKernels`; tests run this driver on CPU tensors over
+    gloo with a stand-in (tests/test_bfs_gloo.py)."""
+
+    def __init__(self, puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv | None = None, *, device="cuda", group=None,
+                 ctas_per_sm: int | None = None, queue_smem: int | None = None, fallback_table_capacity: int = 1 << 24,
+                 kernels=None, n_puzzles: int | None = None, fallback=None):
+        if kernels is None:
+            table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else \
+                BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
+            kernels = CudaLocalKernels(table, ctas_per_sm, queue_smem)
+            n_puzzles = table.n_envs
+        self.k, self.device, self.group = kernels, kernels.device, group
+        self.n_puzzles = int(n_puzzles)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.fallback_table_capacity = fallback_table_capacity
+        self._fallback = fallback          # (puzzle ids, max_depth, with_paths) -> BfsResult; default: BfsSolver on the CUDA kernels
+
+    def plan(self) -> dict | None:
+        """The launch plan of this rank's shard (None: nothing fits on chip)."""
+        return self.k.plan(*shard_range(self.n_puzzles, self.rank, self.world))
+
+    def _search_rest(self, rest: list[int], max_depth: int, with_paths: bool) -> BfsResult:
+        if self._fallback is not None:
+            return self._fallback(rest, max_depth, with_paths)
+        sub = BatchedTilerSliderEnv.from_puzzles([self.k.puzzle(i) for i in rest], device=self.device)
+        cap = self.fallback_table_capacity
+        while True:
+            try:
+                return BfsSolver(sub, table_capacity=cap, group=self.group).solve(max_depth=max_depth, with_paths=with_paths and self.world == 1)
+            except RuntimeError as e:                     # visited table full: double it
+                if "table" not in str(e) or cap >= 1 << 32:
+                    raise
+                cap *= 2
+
+    def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False) -> BfsResult:
+        dev, P = self.device, self.n_puzzles
+        n_levels, max_moves = getattr(self.k, "N_LEVELS", 256), getattr(self.k, "MAX_MOVES", 255)
+        out = dict(states=torch.zeros(P, dtype=torch.int64, device=dev),
+                   depth=torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev),
+                   status=torch.zeros(P, dtype=torch.int32, device=dev),
+                   levels=torch.zeros(n_levels, dtype=torch.int64, device=dev),
+                   counters=torch.zeros(8, dtype=torch.int64, device=dev),
+                   moves=torch.zeros(P, max_moves, dtype=torch.uint8, device=dev) if with_paths else None,
+                   lengths=torch.full((P,), -(1 << 30), dtype=torch.int32, device=dev) if with_paths else None)
+        lo, hi = shard_range(P, self.rank, self.world)
+        self.k.search(lo, hi, max_depth, out)
+        states_pp, depth_pp, status, levels, counters = out["states"], out["depth"], out["status"], out["levels"], out["counters"]
+        if self.world > 1:              # every puzzle has exactly one owner: sums / maxima over the ranks put the pieces together
             dist.all_reduce(states_pp, group=self.group)
             dist.all_reduce(depth_pp, op=dist.ReduceOp.MAX, group=self.group)
             dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
             dist.all_reduce(levels, group=self.group)
-            dist.all_reduce(counters[1:2], group=self.group)
+            gen = counters[1:2].clone()
+            dist.all_reduce(gen, group=self.group)
+            counters[1:2] = gen
             if with_paths:
-                dist.all_reduce(lengths, op=dist.ReduceOp.MAX, group=self.group)
-                dist.all_reduce(moves, op=dist.ReduceOp.MAX, group=self.group)
+                dist.all_reduce(out["lengths"], op=dist.ReduceOp.MAX, group=self.group)
+                mv32 = out["moves"].to(torch.int32)       # (uint8 reductions are not available on every backend)
+                dist.all_reduce(mv32, op=dist.ReduceOp.MAX, group=self.group)
+                out["moves"] = mv32.to(torch.uint8)
         generated = int(counters[1].item())
         lv = levels.tolist()
         solutions = None
         if with_paths:
-            mv, ln = moves.cpu().tolist(), lengths.cpu().tolist()
+            mv, ln = out["moves"].cpu().tolist(), out["lengths"].cpu().tolist()
             solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
         # ---- puzzles that did not fit on chip: the hash-partitioned search (collective over the same ranks)
         rest = torch.nonzero(status).flatten().tolist()
         if rest:
-            sub = BatchedTilerSliderEnv.from_puzzles([t.puzzle(i) for i in rest], device=dev)
-            cap = self.fallback_table_capacity
-            while True:
-                try:
-                    r = BfsSolver(sub, table_capacity=cap, group=self.group).solve(
-                        max_depth=max_depth, with_paths=with_paths and self.world == 1)
-                    break
-                except RuntimeError as e:                     # visited table full: double it
-                    if "table" not in str(e) or cap >= 1 << 32:
-                        raise
-                    cap *= 2
+            r = self._search_rest(rest, max_depth, with_paths)
             idx = torch.tensor(rest, dtype=torch.int64, device=dev)
-            states_pp[idx] = r.states_per_puzzle
-            depth_pp[idx] = r.solve_depth_per_puzzle.to(torch.int32)
+            states_pp[idx] = r.states_per_puzzle.to(dev)
+            depth_pp[idx] = r.solve_depth_per_puzzle.to(device=dev, dtype=torch.int32)
             generated += r.generated
-            lv = [a_ + b_ for a_, b_ in zip(lv + [0] * max(0, len(r.levels) - len(lv)), r.levels + [0] * max(0, len(lv) - len(r.levels)))]
+            n = max(len(lv), len(r.levels))
+            lv = [(lv[i] if i < len(lv) else 0) + (r.levels[i] if i < len(r.levels) else 0) for i in range(n)]
             if solutions is not None and r.solutions is not None:
                 for j, i in enumerate(rest):
                     solutions[i] = r.solutions[j]
