@@ -19,6 +19,12 @@
  *    thread.  No global mutable state: re-entrant across streams and devices (the caller
  *    selects the device).
  *  - There is no CPU fallback anywhere in this library.
+ *  - Domain: well-formed boards -- tiles on distinct cells, none on a blocked cell (what the
+ *    reference's loaders produce; outside it the reference itself is erratic).  The
+ *    kernels do not check this (tiler_slider_b200.Puzzle.validate does, on the host); a tile placed
+ *    on a blocked cell slides out of it on boards up to 8x8 and 15x15 / 16x16, and stays put on
+ *    9x9 .. 14x14 (the wide slide treats the own cell as wall-free).  GameState.move_to, which is
+ *    defined for blocked start cells, therefore probes on a board whose start cell is open.
  *
  * Packed layout (struct-of-arrays, environment index innermost):
  *  - capacity: allocation stride in environments, a multiple of TS_CAP_ALIGN.  EVERY per-env
