@@ -492,17 +492,19 @@ class Runner:
                          "algorithmic_bytes_per_successor": 42, "peak_source": self.peak_source}}
         del solver
         torch.cuda.empty_cache()
-        if _has_local_bfs():
-            from tiler_slider_b200.bfs import LocalBfs
-            local = LocalBfs(table)
-            resl, (coldl, warml) = run(local)
-            results["local"] = resl
-            out["per_puzzle_on_chip"] = {
-                "value": resl.generated / warml, "seconds": warml, "seconds_cold": coldl, "unique_states": resl.n_states,
-                "generated_successors": resl.generated, "depth": len(resl.levels) - 1,
-                "what": "one CTA per puzzle, visited set = perfect-hash bitmap in shared memory, frontier queue in shared "
-                        "memory (spilling to HBM), puzzles sharded over the ranks with no exchange",
-                "fallback_puzzles": int(getattr(resl, "fallback_puzzles", 0))}
+        from tiler_slider_b200.bfs import LocalBfs
+        local = LocalBfs(table)
+        resl, (coldl, warml) = run(local)
+        results["local"] = resl
+        out["per_puzzle_on_chip"] = {
+            "value": resl.generated / warml, "seconds": warml, "seconds_cold": coldl, "unique_states": resl.n_states,
+            "generated_successors": resl.generated, "depth": len(resl.levels) - 1,
+            "what": "K6: one CTA per puzzle, visited set = perfect-hash bitmap in shared memory, live levels in a shared-memory "
+                    "ring (spilling to HBM), puzzles sharded over the ranks with no exchange",
+            "plan_rank0": local.plan(), "fallback_puzzles": int(resl.fallback_puzzles),
+            "roofline": {"bound": "on-chip (instruction issue / shared-memory latency); the 42 B per successor of SURVEY 8(d) are not moved",
+                         "hbm_equivalent_GBps": 42 * resl.generated / self.world / warml / 1e9,
+                         "dram_bytes_per_search_ncu": "about 1 MB per 65,536 puzzles (profiles/r2_ncu_bfs_local_raw.csv)"}}
         out["value"] = max(v["value"] for k, v in out.items() if isinstance(v, dict) and "value" in v)
         # per-puzzle results against the CPU oracle's BFS (rank 0)
         ok, n_chk = True, 0
@@ -530,14 +532,6 @@ class Runner:
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
-
-
-def _has_local_bfs() -> bool:
-    try:
-        from tiler_slider_b200 import bfs as _b
-        return hasattr(_b, "LocalBfs")
-    except Exception:
-        return False
 
 
 def ncu_traffic(cfg: Config, n_local: int) -> dict | None:
