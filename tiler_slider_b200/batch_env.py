@@ -38,7 +38,7 @@ class BatchedTilerSliderEnv:
     def __init__(self, size: int, n_tiles: int, n_envs: int, multi_color: bool = False, *,
                  max_steps: int = 100, auto_reset: bool = False, device: str | torch.device = "cuda",
                  rewards: Sequence[float] = DEFAULT_REWARDS, track_terminal: bool = False,
-                 n_targets: int | None = None, track_flags: bool = True):
+                 n_targets: int | None = None, track_flags: bool = True, host_io: bool = False):
         if not torch.cuda.is_available():
             raise _lib.TilerSliderError("BatchedTilerSliderEnv needs a CUDA device (no CPU fallback)")
         self._lib = lib()
@@ -86,12 +86,19 @@ class BatchedTilerSliderEnv:
         tbytes = self.pos_bytes if self.goal_mode == GOAL_ORDERED else self._lib.ts_target_board_bytes(self.size)
         self._targets = torch.zeros(cap * tbytes, dtype=u8, device=dev)
         self._init = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev)
-        self._pos = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev)
+        # host_io (the single-env adapter): positions, actions and the step's outputs live in pinned HOST
+        # memory that the kernels address directly (unified addressing), so a step is launches + one
+        # stream synchronisation, with no copy calls; meant for tiny batches, where latency is all
+        self.host_io = bool(host_io)
+
+        def io(*shape, dtype=u8):
+            return torch.zeros(*shape, dtype=dtype, pin_memory=True) if self.host_io else torch.zeros(*shape, dtype=dtype, device=dev)
+        self._pos = io(cap, self.pos_bytes)
         self._count = torch.zeros(cap, dtype=u8 if self.count_bytes == 1 else torch.int32, device=dev)
-        self._actions = torch.zeros(cap, dtype=u8, device=dev)
-        self._reward = torch.zeros(cap, dtype=torch.float32, device=dev)
-        self._done = torch.zeros(cap, dtype=u8, device=dev)
-        self._flags = torch.zeros(cap, dtype=u8, device=dev)
+        self._actions = io(cap)
+        self._reward = io(cap, dtype=torch.float32)
+        self._done = io(cap)
+        self._flags = io(cap)
         self._terminal = torch.zeros(cap, self.pos_bytes, dtype=u8, device=dev) if track_terminal else None
         self._obs_targets = None      # ordered targets of a never_win batch, for observe() / target_positions()
         self._scratch_count = None
@@ -100,6 +107,8 @@ class BatchedTilerSliderEnv:
         self._host_ctx = None
         self._cached_args = None
         self._cached_out = None
+        self._cached_obs_args = None
+        self._io_np = None
         self._loaded = False
 
     # ------------------------------------------------------------------ construction
@@ -236,7 +245,39 @@ class BatchedTilerSliderEnv:
                 rc = self._lib.ts_step(C.byref(a), self._stream())
         if rc:
             check(rc, "ts_step")
+        if self.host_io:          # the outputs are host memory: they are valid once the stream has drained
+            torch.cuda.current_stream(self.device).synchronize()
         return self._cached_out
+
+    def step_host_io(self, action: int, obs_out: torch.Tensor | None = None) -> None:
+        """host_io batches: every env takes `action`; K2 (and K3 into the pinned `obs_out`) are launched
+        and the stream is synchronised -- afterwards pos / reward / done / flags (and obs_out) can be
+        read on the host as they are.  No tensor is created on this path."""
+        if not self.host_io:
+            raise RuntimeError("step_host_io needs a batch built with host_io=True")
+        self._require_loaded()
+        if self._io_np is None:
+            self._io_np = self._actions.numpy()
+        self._io_np[: self.n_envs] = action
+        a = self._cached_args
+        if a is None:
+            a = self._cached_args = self._step_args(self._actions.data_ptr())
+            n = self.n_envs
+            self._cached_out = (self._pos[:n], self._reward[:n], self._done[:n].view(torch.bool))
+        a.d_actions = self._actions.data_ptr()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            rc = self._lib.ts_step(C.byref(a), stream.cuda_stream)
+            if rc:
+                check(rc, "ts_step")
+            if obs_out is not None:
+                o = self._cached_obs_args
+                if o is None or o.d_obs != obs_out.data_ptr():
+                    o = self._cached_obs_args = self._observe_args(obs_out)
+                rc = self._lib.ts_observe(C.byref(o), stream.cuda_stream)
+                if rc:
+                    check(rc, "ts_observe")
+            stream.synchronize()
 
     def capture_steps(self, action_rows: torch.Tensor) -> "torch.cuda.CUDAGraph":
         """Capture `len(action_rows)` consecutive steps (row k = the actions of step k, uint8
@@ -413,15 +454,18 @@ class BatchedTilerSliderEnv:
         if out is None:
             out = torch.empty(n, S, S, 3, dtype=torch.float32, device=self.device)
         # single colour with one tile is stored as an ordered batch: index+1 == 1, same values
-        # a never_win batch draws its ordered targets from their own buffer (count != tile count)
-        nt = 0 if self._obs_targets is None else (self.n_targets or -1)
-        tg = self._targets if self._obs_targets is None else self._obs_targets
-        a = ObserveArgs(size=S, n_tiles=self.n_tiles, goal_mode=self.goal_mode, n_targets=nt,
-                        first_env=0, n_envs=n, capacity=self.capacity, d_walls=_ptr(self._walls),
-                        d_targets_packed=_ptr(tg), d_pos=_ptr(self._pos), d_obs=_ptr(out))
+        a = self._observe_args(out)
         with torch.cuda.device(self.device):
             check(self._lib.ts_observe(C.byref(a), self._stream()), "ts_observe")
         return out
+
+    def _observe_args(self, out: torch.Tensor) -> ObserveArgs:
+        # a never_win batch draws its ordered targets from their own buffer (count != tile count)
+        nt = 0 if self._obs_targets is None else (self.n_targets or -1)
+        tg = self._targets if self._obs_targets is None else self._obs_targets
+        return ObserveArgs(size=self.size, n_tiles=self.n_tiles, goal_mode=self.goal_mode, n_targets=nt,
+                           first_env=0, n_envs=self.n_envs, capacity=self.capacity, d_walls=_ptr(self._walls),
+                           d_targets_packed=_ptr(tg), d_pos=_ptr(self._pos), d_obs=_ptr(out))
 
     def valid_moves(self) -> torch.Tensor:
         """uint8[N]: bit d set when move d changes the state (get_valid_moves,

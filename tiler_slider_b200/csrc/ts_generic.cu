@@ -16,11 +16,6 @@
 
 namespace ts {
 
-// bit `bit` of env's board in a plane-layout buffer
-__device__ __forceinline__ bool board_bit(const uint8_t* base, int nb, size_t cap, size_t env, int bit) {
-    return (base[board_byte_addr(nb, cap, env, bit >> 3)] >> (bit & 7)) & 1;
-}
-
 __global__ void __launch_bounds__(128) generic_step_kernel(const ts_step_args a) {
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= a.n_envs) return;
@@ -33,14 +28,15 @@ __global__ void __launch_bounds__(128) generic_step_kernel(const ts_step_args a)
     for (int t = 0; t < T; ++t) p[t] = p0[t] = a.d_pos[env * pw + t];
     bool moved = false;
     if (T > 0) {                                   // bitboard classes only (ts_step never sends wide boards with tiles here)
-        uint64_t occ = 0;
+        uint64_t walls = 0, occ = 0;               // the whole board in one word (independent byte loads), then register bit tests
+        for (int b = 0; b < nb; ++b) walls |= (uint64_t)a.d_walls[board_byte_addr(nb, cap, env, b)] << (8 * b);
         for (int t = 0; t < T; ++t) occ |= 1ull << ((p0[t] / ps) * bs + p0[t] % ps);
         for (int t = 0; t < T; ++t) {
             const int r = p0[t] / ps, c = p0[t] % ps;
             int n = 0;
             for (int rr = r + dr, cc = c + dc; rr >= 0 && rr < S && cc >= 0 && cc < S; rr += dr, cc += dc) {
                 const int bit = rr * bs + cc;
-                if (board_bit(a.d_walls, nb, cap, env, bit)) break;
+                if ((walls >> bit) & 1ull) break;
                 if (!((occ >> bit) & 1ull)) ++n;
             }
             p[t] = (uint8_t)((r + n * dr) * ps + (c + n * dc));

@@ -63,10 +63,16 @@ class GameState:
         if self._batch_obj is None:
             p = Puzzle(self.size, self._blocked, [(int(r), int(c)) for r, c in self._initial],
                        [(int(r), int(c)) for r, c in self.target_locations], bool(self.multi_color))
-            self._batch_obj = BatchedTilerSliderEnv.from_puzzles([p], max_steps=self._max_steps, auto_reset=False,
-                                                                 device=self._device)
+            # host_io: positions and step outputs in pinned host memory the kernels write directly -- a
+            # step of this batch of one is two launches and a stream synchronisation, no copies
+            b = self._batch_obj = BatchedTilerSliderEnv.from_puzzles([p], max_steps=self._max_steps, auto_reset=False,
+                                                                     device=self._device, host_io=True)
+            self._np_pos, self._np_flags, self._np_reward = b._pos.numpy(), b._flags.numpy(), b._reward.numpy()
+            self._obs_pinned = torch.zeros(1, self.size, self.size, 3, dtype=torch.float32, pin_memory=True)
+            self._np_obs = self._obs_pinned.numpy()
+            self._obs_fresh = False
             if self._locs != self._initial:      # positions assigned before the first use
-                self._batch_obj.set_positions(torch.tensor([[list(map(int, rc)) for rc in self._locs]], dtype=torch.uint8))
+                b.set_positions(torch.tensor([[list(map(int, rc)) for rc in self._locs]], dtype=torch.uint8))
         return self._batch_obj
 
     # -- positions ------------------------------------------------------------------------
@@ -75,8 +81,10 @@ class GameState:
         """List of (row, col) per tile (the reference's become numpy ints after a move;
         compare by value)."""
         if self._dirty:
-            rc = self._batch.positions()[0].cpu().tolist()
-            self._locs = [(int(r), int(c)) for r, c in rc]
+            b = self._batch
+            torch.cuda.current_stream(b.device).synchronize()      # the kernels write positions straight into host memory
+            ps = b.pos_stride
+            self._locs = [(int(v) // ps, int(v) % ps) for v in self._np_pos[0, : b.n_tiles]]
             self._dirty = False
         return self._locs
 
@@ -85,20 +93,22 @@ class GameState:
         self._locs = list(locs)
         self._dirty = False
         if self._batch_obj is not None:
+            self._obs_fresh = False
             self._batch_obj.set_positions(torch.tensor([[list(map(int, rc)) for rc in locs]], dtype=torch.uint8))
 
     # -- the move path ----------------------------------------------------------------------
     def move(self, move: Move) -> bool:
         """state.py:120-170 on the GPU; returns is_won()."""
         flags = self._batch.raw_move(torch.tensor([move.value], dtype=torch.uint8))
-        self._dirty = True
+        self._dirty, self._obs_fresh = True, False
         return bool(int(flags[0]) & F_WON)
 
     def _env_step(self, move: Move) -> int:
-        """One bookkept step (K2 with the env's max_steps); returns the flag byte."""
-        self._batch.step(torch.tensor([move.value], dtype=torch.uint8))
-        self._dirty = True
-        return int(self._batch.flags[0])
+        """One bookkept step (K2 with the env's max_steps) plus the observation of the new state (K3),
+        both written by the kernels into pinned host memory; returns the flag byte."""
+        self._batch.step_host_io(move.value, self._obs_pinned)
+        self._dirty, self._obs_fresh = True, True
+        return int(self._np_flags[0])
 
     def is_won(self) -> bool:
         """state.py:172-186 on the current positions (ts_goal_check)."""
@@ -106,7 +116,12 @@ class GameState:
 
     def get_state_array(self) -> np.ndarray:
         """state.py:188-211: float32[S,S,3] from K3."""
-        return self._batch.observe()[0].cpu().numpy()
+        b = self._batch
+        if not self._obs_fresh:
+            b.observe(self._obs_pinned)
+            torch.cuda.current_stream(b.device).synchronize()
+            self._obs_fresh = True
+        return self._np_obs[0].copy()
 
     @property
     def move_to(self) -> np.ndarray:
@@ -183,7 +198,7 @@ class TilerSliderEnv:
             raise TypeError(f"Action must be a GameState.Move enum, got {type(move)}")
         flags = self.state._env_step(move)
         won, invalid, timeout = bool(flags & F_WON), bool(flags & F_INVALID), bool(flags & F_TIMEOUT)
-        self.last_reward = float(self.state._batch.reward[0])
+        self.last_reward = float(self.state._np_reward[0])
         info = {"is_won": won, "step_count": self.step_count, "invalid_move": invalid}
         if won:
             self.done = True
