@@ -6,7 +6,8 @@ Public surface (reference names kept):
   BatchedTilerSliderEnv                              N boards per GPU, one kernel launch per step
   Puzzle, parse_board_text, load_puzzle_file         text grammar + `-input_file` loader
   levels.load_level / load_level_image               screenshot ingest (host-side, cv2)
-  bfs.BfsSolver                                      batched breadth-first search, NCCL dedup
+  bfs.LocalBfs                                       batched breadth-first search, one CTA per puzzle, on chip
+  bfs.BfsSolver                                      hash-partitioned search (HBM table, NVLink / NCCL exchange)
 Every computation runs in libtiler_slider.so (hand-written sm_100a CUDA, C-ABI in
 include/tiler_slider.h); there is no CPU fallback.
 """
@@ -16,7 +17,7 @@ from .puzzle import Puzzle, load_puzzle_file, parse_board_text, parse_puzzle_fil
 from .batch_env import DEFAULT_REWARDS, BatchedTilerSliderEnv, shard_range
 from .env import GameState, TilerSliderEnv, TilerSliderEnvFactory
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["GameState", "TilerSliderEnv", "TilerSliderEnvFactory", "Move", "BatchedTilerSliderEnv", "Puzzle",
            "parse_board_text", "parse_puzzle_file_text", "load_puzzle_file", "puzzle_to_text", "shard_range",
            "DEFAULT_REWARDS", "TilerSliderError", "build", "lib",
