@@ -40,22 +40,24 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_a
         reinterpret_cast<float4*>(stage)[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();
 
-    // walls (and set-goal targets): one bit test per cell
-    for (int j = threadIdx.x; j < n_here * CELLS; j += OBS_THREADS) {
-        const int e = j / CELLS, cell = j - e * CELLS;
-        const int r = cell / S, c = cell - r * S;
+    // walls (and set-goal targets): one work item per (env, row) -- the row's bits are fetched once and
+    // only the SET bits are visited (a board is mostly empty: 8 walls in 36 cells), instead of one
+    // board load and one bit test per cell
+    for (int j = threadIdx.x; j < n_here * S; j += OBS_THREADS) {
+        const int e = j / S, r = j - e * S;
         const size_t env = (size_t)(a.first_env + env0 + e);
-        bool wall, tgt = false;
+        uint32_t wrow, trow = 0;
         if constexpr (wide_board(S)) {
-            wall = (reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * (2 * wide_line_words(S)) + r] >> (c + wide_line_lead(S))) & 1;   // plane 1 = rows
-            if (!ordered) tgt = (reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * WIDE_TARGET_WORDS + r] >> c) & 1;
+            wrow = (uint32_t)reinterpret_cast<const uint16_t*>(a.d_walls)[(cap + env) * (2 * wide_line_words(S)) + r] >> wide_line_lead(S);   // plane 1 = rows
+            if (!ordered) trow = reinterpret_cast<const uint16_t*>(a.d_targets_packed)[env * WIDE_TARGET_WORDS + r];
         } else {
-            const int bit = r * board_stride(S) + c;
-            wall = (load_board_elem<NB>(a.d_walls, cap, env) >> bit) & 1ull;
-            if (!ordered) tgt = (load_board_elem<NB>(a.d_targets_packed, cap, env) >> bit) & 1ull;
+            wrow = (uint32_t)(load_board_elem<NB>(a.d_walls, cap, env) >> (r * board_stride(S)));
+            if (!ordered) trow = (uint32_t)(load_board_elem<NB>(a.d_targets_packed, cap, env) >> (r * board_stride(S)));
         }
-        if (wall) stage[j * 3] = 1.0f;
-        if (tgt) stage[j * 3 + 2] = 1.0f;
+        constexpr uint32_t ROW = (1u << S) - 1u;      // drops the sentinels past column S-1
+        float* img = stage + (e * CELLS + r * S) * 3;
+        for (uint32_t m = wrow & ROW; m; m &= m - 1u) img[(__ffs(m) - 1) * 3] = 1.0f;
+        for (uint32_t m = trow & ROW; m; m &= m - 1u) img[(__ffs(m) - 1) * 3 + 2] = 1.0f;
     }
     // tiles and ordered targets: one thread per env, ascending index (later overwrites earlier).
     // Ordered targets: n_targets = 0 means "as many as tiles, packed like the position word";
@@ -79,9 +81,26 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const ts_observe_a
             }
         }
     }
-    __syncthreads();
-
     float* out = a.d_obs + env0 * PER_ENV;          // 16-byte aligned: E * PER_ENV is a multiple of 4
+#ifndef TS_OBS_NO_BULK
+    // Stream-out by the copy engine of the SM: one elected thread hands the whole staged image
+    // (up to 28 KB, contiguous in HBM) to cp.async.bulk (TMA 1-D, SASS UBLKCP) instead of 256 threads
+    // looping over 16-byte stores.  The writers publish their shared-memory stores to the async
+    // proxy first; the issuing thread stays until the engine has read the stage.  (A block whose
+    // image is not a multiple of 16 bytes -- the ragged last block of an odd board size -- keeps the loop.)
+    if ((n_floats & 3) == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(out), "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"((uint32_t)n_floats * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+#endif
+    __syncthreads();
     for (int k = threadIdx.x; k * 4 < n_floats; k += OBS_THREADS) {
         if (k * 4 + 3 < n_floats) __stcs(reinterpret_cast<float4*>(out) + k, reinterpret_cast<const float4*>(stage)[k]);
         else for (int j = k * 4; j < n_floats; ++j) out[j] = stage[j];
