@@ -1,11 +1,29 @@
 // ts_valid.cuh -- per-env mask of the moves that change the state
 // (TilerSliderEnv.get_valid_moves, explainrl/environment/environment.py:149-171), computed
-// by running the slide core for all four directions in registers.
+// from the occupancy and wall bitboards with four shifts (no slide is run).
 #pragma once
 #include "ts_common.cuh"
 #include "../../include/tiler_slider.h"
 
 namespace ts {
+
+// A move changes the state iff SOME tile has an empty cell right ahead of it: a tile whose next cell
+// is a wall or the edge stays, a tile behind another tile moves exactly when that one does, and the
+// chain ends at a wall -- so "nothing moves" == "no tile faces an empty cell".  Four shifts of the
+// occupancy board instead of four slides (get_valid_moves itself copies the state and tries the
+// four moves, environment.py:162-169; same answers, checked against the oracle).
+template <int S> __device__ __forceinline__ uint32_t valid_mask_of(uint64_t occ, uint64_t walls) {
+    constexpr int BS = board_stride(S);
+    constexpr uint64_t CELLS = [] { uint64_t m = 0; for (int r = 0; r < S; ++r) for (int c = 0; c < S; ++c) m |= 1ull << (r * BS + c); return m; }();
+    constexpr uint64_t COL0 = [] { uint64_t m = 0; for (int r = 0; r < S; ++r) m |= 1ull << (r * BS); return m; }();
+    const uint64_t open = CELLS & ~walls & ~occ;               // cells a tile can enter (sentinels and bits past the board excluded)
+    uint64_t left = occ >> 1, right = occ << 1;
+    if constexpr (!padded_board(S)) {                          // compact boards have no sentinel column between the rows
+        left = (occ & ~COL0) >> 1;
+        right = (occ & ~(COL0 << (S - 1))) << 1;
+    }
+    return ((occ >> BS) & open ? 1u : 0u) | ((occ << BS) & open ? 2u : 0u) | (left & open ? 4u : 0u) | (right & open ? 8u : 0u);
+}
 
 template <int S, int T>
 __global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_valid_args a) {
@@ -25,18 +43,7 @@ __global__ void __launch_bounds__(256) valid_kernel(const __grid_constant__ ts_v
         uint32_t q0[PR], bw[NWORDS];
         group_elem<PW>(praw, e, q0);
         walls.get(e, bw);
-        const uint64_t wb = board64(bw);
-#pragma unroll
-        for (uint32_t d = 0; d < 4; ++d) {
-            uint32_t q[PR];
-#pragma unroll
-            for (int w = 0; w < PR; ++w) q[w] = q0[w];
-            slide_env<S, T>(q, wb, d >> 1, (d & 1u) ^ 1u);
-            bool moved = false;
-#pragma unroll
-            for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
-            mask4 |= (moved ? 1u : 0u) << (8 * e + d);
-        }
+        mask4 |= valid_mask_of<S>(occupancy<S, T>(q0), board64(bw)) << (8 * e);
     }
     __stcs(reinterpret_cast<unsigned int*>(a.d_mask + e0), mask4);
 }

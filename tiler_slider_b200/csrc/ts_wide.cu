@@ -289,6 +289,42 @@ __global__ void __launch_bounds__(WIDE_THREADS, WIDE_MIN_BLOCKS) wide_step_kerne
     if (a.d_flags) a.d_flags[env] = (uint8_t)flags;
 }
 
+// Valid-move mask of a wide board without running a slide (see valid_mask_of, ts_valid.cuh): a move
+// changes the state iff some tile has an empty cell right ahead.  Occupancy rows are built in the
+// thread's shared-memory column (pair words: rows 2k | 2k+1 << 16, cell c at bit c), the wall rows come
+// from the rows plane alone; LEFT / RIGHT shift inside the rows, UP / DOWN shift the rows past each
+// other with one funnel shift per pair word.
+template <int T, int LW>
+__device__ __forceinline__ uint32_t valid_mask_wide(WideSmem& sm, const uint32_t (&q)[(T + 3) / 4], const uint32_t* rows_rec, int S) {
+    uint32_t* ocol = &sm.o[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < LW; ++k) ocol[k * WIDE_THREADS] = 0;
+    static_for<0, T>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t b = byte_of<i % 4>(q[i / 4]);          // row * 16 + col
+        atomicOr(ocol + (b >> 5) * WIDE_THREADS, 1u << ((b & 15u) + (b & 16u)));
+    });
+    const uint32_t lead = LW == 8 ? 0u : 1u;                     // S <= 14: cells at bits 1..S between two sentinels
+    const uint32_t row_cells = (1u << S) - 1u;
+    uint32_t o[LW + 2], open[LW];
+    o[0] = o[LW + 1] = 0;
+#pragma unroll
+    for (int k = 0; k < LW; ++k) {
+        o[k + 1] = ocol[k * WIDE_THREADS];
+        const uint32_t cells = row_cells | ((2 * k + 1 < S ? row_cells : 0u) << 16);     // the rows this pair really has
+        open[k] = cells & ~(__ldg(rows_rec + k) >> lead) & ~o[k + 1];
+    }
+    uint32_t up = 0, down = 0, left = 0, right = 0;
+#pragma unroll
+    for (int k = 0; k < LW; ++k) {
+        up |= __funnelshift_r(o[k + 1], o[k + 2], 16) & open[k];      // row r+1 seen from row r
+        down |= __funnelshift_l(o[k], o[k + 1], 16) & open[k];        // row r-1 seen from row r
+        left |= ((o[k + 1] >> 1) & 0x7FFF7FFFu) & open[k];
+        right |= ((o[k + 1] << 1) & 0xFFFEFFFEu) & open[k];
+    }
+    return (up ? 1u : 0u) | (down ? 2u : 0u) | (left ? 4u : 0u) | (right ? 8u : 0u);
+}
+
 template <int T>
 __global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_constant__ ts_valid_args a) {
     constexpr int PW = pos_bytes(T), PR = (T + 3) / 4;
@@ -298,23 +334,14 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_valid_kernel(const __grid_c
     const size_t env = (size_t)(a.first_env + i);
     uint32_t q0[PR];
     ld_pos<PW>(a.d_pos, env, q0);
-    uint32_t mask = 0;
-    for (uint32_t d = 0; d < 4; ++d) {
-        uint32_t q[PR];
-#pragma unroll
-        for (int w = 0; w < PR; ++w) q[w] = q0[w];
-        const int lw = wide_line_words(a.size);
-        const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.d_walls) + ((size_t)(d >> 1) * (size_t)a.capacity + env) * (size_t)lw;
-        switch (lw) {
-            case 5: slide_wide<T, 5>(sm, q, rec, d); break;
-            case 6: slide_wide<T, 6>(sm, q, rec, d); break;
-            case 7: slide_wide<T, 7>(sm, q, rec, d); break;
-            default: slide_wide16<T>(sm, q, reinterpret_cast<const uint4*>(rec), a.size, d); break;
-        }
-        bool moved = false;
-#pragma unroll
-        for (int w = 0; w < PR; ++w) moved |= q[w] != q0[w];
-        mask |= (moved ? 1u : 0u) << d;
+    const int lw = wide_line_words(a.size);
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.d_walls) + ((size_t)a.capacity + env) * (size_t)lw;   // plane 1 = rows
+    uint32_t mask;
+    switch (lw) {
+        case 5: mask = valid_mask_wide<T, 5>(sm, q0, rec, a.size); break;
+        case 6: mask = valid_mask_wide<T, 6>(sm, q0, rec, a.size); break;
+        case 7: mask = valid_mask_wide<T, 7>(sm, q0, rec, a.size); break;
+        default: mask = valid_mask_wide<T, 8>(sm, q0, rec, a.size); break;
     }
     a.d_mask[env] = (uint8_t)mask;
 }
