@@ -1,3 +1,6 @@
+"""Kernel-only timing of ts_valid_moves (prebuilt argument block, CUDA events): python profiles/experiments/valid_kernel_time.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes as C, torch, tiler_slider_b200 as ts
 from tiler_slider_b200._lib import ValidArgs, GoalArgs
 lib = ts.lib()
