@@ -201,11 +201,13 @@ def parity_check(ts, dev, cfg: Config, n_envs: int = 8192, steps: int = 128) -> 
     want = orc.rollout(S, multi, blocked, tiles, targets, actions[:, :n_envs].cpu().numpy(), max_steps=MAX_STEPS, auto_reset=True)
     bad = fast_bad = 0
     for k in range(steps):
+        count_before = env.step_count.to(torch.int32).cpu().numpy()      # info['step_count'] is pre-increment (environment.py:128)
         _, r, d = env.step(actions[k])
         post = torch.where(d[:, None, None], env.positions(env.terminal_pos), env.positions())
         bad += int((post.cpu().numpy() != want["pos"][k]).any(axis=(1, 2)).sum())
         bad += int((env.flags.cpu().numpy() != want["flags"][k]).sum())
         bad += int((r.cpu().numpy() != want["reward"][k]).sum())
+        bad += int((count_before != want["count"][k]).sum())
         _, rf, df = fast.step(actions[k])
         fast_bad += int(not torch.equal(fast.pos, env.pos)) + int(not torch.equal(rf, r)) + int(not torch.equal(df, d))
     # K3 / valid-move mask of the states the rollout ended in (first n_obs envs), against the oracle
@@ -219,7 +221,7 @@ def parity_check(ts, dev, cfg: Config, n_envs: int = 8192, steps: int = 128) -> 
         obs_bad += int((st.get_state_array() != obs[i]).any())
         obs_bad += int(sum(1 << d for d in st.valid_moves()) != int(valid[i]))
     return {"env_steps_checked": n_envs * steps, "mismatches": bad, "fast_path_mismatches": fast_bad,
-            "fields": "positions, flags (done/won/invalid/timeout), reward",
+            "fields": "positions per tile, flags (done/won/invalid/timeout), reward, pre-increment step_count",
             "observations_checked": n_obs, "observation_or_valid_mask_mismatches": obs_bad,
             "checker": "oracle/ts_oracle.c"}
 
