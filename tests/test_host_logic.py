@@ -158,7 +158,7 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     from tiler_slider_b200 import _lib
     pairs = {"ts_encode_args": _lib.EncodeArgs, "ts_synth_args": _lib.SynthArgs, "ts_step_args": _lib.StepArgs,
              "ts_observe_args": _lib.ObserveArgs, "ts_valid_args": _lib.ValidArgs, "ts_goal_args": _lib.GoalArgs,
-             "ts_bfs_args": _lib.BfsArgs}
+             "ts_bfs_args": _lib.BfsArgs, "ts_bfs_local_args": _lib.BfsLocalArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tiler_slider.h"', 'int main(void) {']
     for cname, mirror in pairs.items():
         lines.append(f'printf("SIZEOF {cname} - %zu\\n", sizeof({cname}));')
