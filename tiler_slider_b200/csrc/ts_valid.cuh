@@ -11,7 +11,7 @@ namespace ts {
 // is a wall or the edge stays, a tile behind another tile moves exactly when that one does, and the
 // chain ends at a wall -- so "nothing moves" == "no tile faces an empty cell".  Four shifts of the
 // occupancy board instead of four slides (get_valid_moves itself copies the state and tries the
-// four moves, environment.py:162-169; same answers, checked against the oracle).
+// four moves, environment.py:162-169; same answers, held by the parity tests).
 template <int S> __device__ __forceinline__ uint32_t valid_mask_of(uint64_t occ, uint64_t walls) {
     constexpr int BS = board_stride(S);
     constexpr uint64_t CELLS = [] { uint64_t m = 0; for (int r = 0; r < S; ++r) for (int c = 0; c < S; ++c) m |= 1ull << (r * BS + c); return m; }();
