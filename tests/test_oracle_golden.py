@@ -325,3 +325,27 @@ def test_level_corpus_bfs():
         assert (n, lv, depth) == (g["n_states"], g["levels"], g["solve_depth"]), g["index"]
     solved = sum(orc.OracleState(*lv).bfs()[2] > 0 for lv in levels)
     assert solved == 400
+
+
+def test_valid_move_rule_used_by_the_kernels():
+    """The valid-move kernels run no slide: they use 'a move changes the state iff some tile has an
+    empty cell right ahead of it' (ts_valid.cuh).  Pin that rule on the CPU against the oracle's
+    copy-and-try get_valid_moves (environment.py:149-171) on random boards of every size."""
+    rng = np.random.default_rng(2)
+    delta = [(-1, 0), (1, 0), (0, -1), (0, 1)]
+    n = 0
+    for S in range(1, 17):
+        for _ in range(40):
+            cells = rng.permutation(S * S)
+            W = int(rng.integers(0, max(1, S * S // 3) + 1))
+            T = int(rng.integers(0, min(8, S * S - W) + 1))
+            blocked = [(int(c) // S, int(c) % S) for c in cells[:W]]
+            tiles = [(int(c) // S, int(c) % S) for c in cells[W:W + T]]
+            st = orc.OracleState(S, blocked, tiles, tiles, False)
+            occ, wall = set(tiles), set(blocked)
+            rule = [d for d, (dr, dc) in enumerate(delta)
+                    if any(0 <= r + dr < S and 0 <= c + dc < S and (r + dr, c + dc) not in wall and (r + dr, c + dc) not in occ
+                           for r, c in tiles)]
+            assert rule == st.valid_moves(), (S, blocked, tiles)
+            n += 1
+    assert n == 640
