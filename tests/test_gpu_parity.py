@@ -618,3 +618,34 @@ def test_baseline_configs_at_their_literal_sizes(ts, S, T, W, multi, N, seed):
     env.step(same)
     assert torch.equal(env.pos[live & ~env.done], before[live & ~env.done])
     assert bool(((env.flags & F_INVALID) != 0)[live].all())
+
+
+def test_fuzz_random_shapes_vs_oracle(ts):
+    """Seeded fuzz over the whole shape space the kernels cover: board size 1..16, 0..8 tiles, target
+    counts equal to / different from the tile count, duplicate targets, both colour modes, auto-reset
+    on / off, step limits around the counter-width boundaries, batch sizes that are not multiples of
+    4 -- every field of every step against the oracle."""
+    rng = np.random.default_rng(20261018)
+    n_cases = 0
+    for case in range(70):
+        S = int(rng.integers(1, 17))
+        T = int(rng.integers(0, min(8, S * S) + 1))
+        W = int(rng.integers(0, max(1, (S * S - T) // 2) + 1)) if S * S - T > 0 else 0
+        multi = bool(rng.integers(0, 2))
+        NT = T if rng.random() < 0.6 else int(rng.integers(0, min(8, S * S) + 1))
+        auto_reset = bool(rng.integers(0, 2))
+        max_steps = int(rng.choice([1, 2, 5, 17, 100, 254, 255, 256, 300]))
+        N, K = int(rng.integers(1, 700)), int(rng.integers(4, 40))
+        perm = np.argsort(rng.random((N, S * S)), axis=1)
+        blocked = np.zeros((N, S * S), np.uint8)
+        np.put_along_axis(blocked, perm[:, :W], 1, axis=1)
+        tc = perm[:, W:W + T]
+        tiles = np.stack([tc // S, tc % S], -1).astype(np.uint8)
+        gc = rng.integers(0, S * S, size=(N, NT))                       # targets anywhere: under tiles, on walls, duplicated
+        targets = np.stack([gc // S, gc % S], -1).astype(np.uint8)
+        actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+        want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=max_steps, auto_reset=auto_reset)
+        got = run_gpu(ts, S, multi, blocked, tiles, targets, actions, max_steps, auto_reset)
+        assert_same(got, want, f"fuzz case {case}: S{S} T{T} NT{NT} W{W} multi{multi} ar{auto_reset} ms{max_steps} N{N}")
+        n_cases += 1
+    assert n_cases == 70
