@@ -96,11 +96,11 @@ def main(argv=None) -> int:
         res = run_puzzle(p, moves, max_steps, args.quiet)
         print(f"result[{k}]: {res}")
         if args.solve:
-            from tiler_slider_b200.bfs import BfsSolver
-            if p.size > 8:
-                print(f"solution[{k}]: BFS supports board sizes up to 8")
+            from tiler_slider_b200.bfs import solve_batch
+            if p.size > 8 or not p.initial_locations:
+                print(f"solution[{k}]: BFS supports board sizes up to 8 with at least one tile")
             else:
-                r = BfsSolver([p], table_capacity=1 << 22).solve(with_paths=True)
+                r = solve_batch([p], with_paths=True)
                 print(f"solution[{k}]: {r.solutions[0]!r} (depth {r.solve_depth}, {r.n_states} reachable states)")
     return 0
 

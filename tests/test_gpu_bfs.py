@@ -305,3 +305,19 @@ def test_local_bfs_level_corpus(ts):
             assert _replay((S, p.blocked_locations, p.initial_locations, p.target_locations, multi), sol) == [depth]
             n_checked += 1
     assert n_checked == 400
+
+
+def test_solve_batch_picks_the_search_that_fits(ts, golden_misc):
+    """bfs.solve_batch: up to 4 tiles -> the on-chip search; 5..8 tiles -> the hash-partitioned search,
+    puzzle by puzzle (its key has no room for a puzzle id).  Same answers as the oracle either way."""
+    from tiler_slider_b200.bfs import solve_batch
+    gold = {b["name"]: b for b in golden_misc["bfs"]}
+    r = solve_batch([puzzle_of(ts, gold["puzzle_multi_111"]), puzzle_of(ts, gold["puzzle_multi_180"])], with_paths=True)
+    assert r.states_per_puzzle.tolist() == [558, 950] and r.solve_depth_per_puzzle.tolist() == [8, 13] and [len(s) for s in r.solutions] == [8, 13]
+    five = [ts.Puzzle(5, [(2, 2), (0, 3)], [(0, 0), (0, 1), (1, 0), (4, 4), (3, 3)], [(4, 0), (4, 1), (4, 2), (4, 3), (0, 4)], False),
+            ts.Puzzle(5, [(1, 1)], [(0, 0), (0, 1), (2, 0), (4, 4), (3, 3)], [(4, 0), (4, 1), (4, 2), (4, 3), (0, 4)], False)]
+    r5 = solve_batch(five)
+    for i, p in enumerate(five):
+        n, lv, depth, _ = orc.OracleState(5, p.blocked_locations, p.initial_locations, p.target_locations, False).bfs(max_states=1 << 20)
+        assert int(r5.states_per_puzzle[i]) == n and int(r5.solve_depth_per_puzzle[i]) == depth
+    assert r5.n_states == int(r5.states_per_puzzle.sum())

@@ -763,6 +763,32 @@ class LocalBfs:
                          generated=generated, solutions=solutions, fallback_puzzles=len(rest))
 
 
+def solve_batch(puzzles: Sequence[Puzzle] | BatchedTilerSliderEnv, *, max_depth: int = 1 << 20, with_paths: bool = False,
+                device="cuda", group=None) -> BfsResult:
+    """BFS of a batch of puzzles of one shape with whichever search fits: the on-chip search (K6,
+    `LocalBfs`) for up to 4 tiles -- puzzles that outgrow it fall back by themselves -- and the
+    hash-partitioned search (`BfsSolver`) for 5 to 8 tiles, where the key has no room for a puzzle id
+    and the puzzles are searched one after the other."""
+    table = puzzles if isinstance(puzzles, BatchedTilerSliderEnv) else BatchedTilerSliderEnv.from_puzzles(list(puzzles), device=device)
+    if table.size > 8:
+        raise ValueError("BFS supports board sizes up to 8")
+    if 1 <= table.n_tiles <= 4:
+        return LocalBfs(table, group=group).solve(max_depth=max_depth, with_paths=with_paths)
+    if table.n_envs == 1:
+        return BfsSolver(table, group=group).solve(max_depth=max_depth, with_paths=with_paths)
+    parts = [BfsSolver([table.puzzle(i)], device=table.device, group=group).solve(max_depth=max_depth, with_paths=with_paths)
+             for i in range(table.n_envs)]
+    n = max(len(r.levels) for r in parts)
+    solved = [r.solve_depth for r in parts if r.solve_depth >= 0]
+    return BfsResult(n_states=sum(r.n_states for r in parts),
+                     levels=[sum(r.levels[d] for r in parts if d < len(r.levels)) for d in range(n)],
+                     solve_depth=min(solved) if solved else -1,
+                     states_per_puzzle=torch.cat([r.states_per_puzzle for r in parts]),
+                     solve_depth_per_puzzle=torch.cat([r.solve_depth_per_puzzle for r in parts]),
+                     generated=sum(r.generated for r in parts),
+                     solutions=[r.solutions[0] for r in parts] if with_paths else None)
+
+
 def solve_puzzle(puzzle: Puzzle, **kw) -> BfsResult:
     """BFS of one puzzle on the current CUDA device."""
     return BfsSolver([puzzle], **kw).solve()
