@@ -374,6 +374,7 @@ class Runner:
             busy_ms += est_ms
             ramp_blocks += 1
         n_blocks = int(max(5, min(max_blocks, budget_s * 1e3 / max(est_ms, 1e-3))))
+        n_blocks = int(min(r[0] for r in self.gather([float(n_blocks)])))     # the same count on every rank
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_blocks)]
         stops = [torch.cuda.Event(enable_timing=True) for _ in range(n_blocks)]
         self.barrier()
@@ -417,7 +418,6 @@ class Runner:
         if traffic:
             out["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
             out["roofline"]["traffic_source"] = traffic["source"]
-        self._last_env = env
         return out
 
     # ---- end to end through host buffers -----------------------------------------------------
