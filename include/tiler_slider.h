@@ -34,7 +34,7 @@
  *    ragged end (n_envs % 4 envs) through a per-env kernel.  The pure queries ts_valid_moves and
  *    ts_goal_check may also WRITE their (correct) result for the up-to-3 envs that share the last
  *    4-env group of the range.
- *  - position word: ts_pos_bytes(T) in {1,2,4,8} bytes per env, byte i = row*PS + col of tile
+ *  - position word: ts_pos_bytes(T) in {1,2,4,8,16,32} bytes per env, byte i = row*PS + col of tile
  *    i (PS = ts_pos_stride(S)), unused bytes zero.  Arrays: pos (in/out), init, targets
  *    (ordered mode).
  *  - board: bitboard of ts_board_bytes(S) bytes per env, bit row*BS + col (BS =
@@ -65,7 +65,7 @@ extern "C" {
 #define TS_VERSION 200          /* 0.2.0 */
 #define TS_CAP_ALIGN 128
 #define TS_MAX_SIZE 16
-#define TS_MAX_TILES 8
+#define TS_MAX_TILES 32         /* 0..8: register kernels; 9..32: per-env generic kernels (csrc/ts_generic.cu) */
 
 /* flag bits of the per-env status byte */
 #define TS_F_DONE 1u      /* environment.py:133-141  done = is_won or step_count >= max_steps */
@@ -104,7 +104,7 @@ int ts_target_board_bytes(int size); /* bytes per env of the set-goal target boa
 int ts_plane_count(int n_bytes);
 int ts_plane_width(int n_bytes, int k);
 int ts_plane_offset(int n_bytes, int k);
-/* 1 if ts_step covers (size, n_tiles): 1 <= size <= 16, 0 <= n_tiles <= 8, else 0 */
+/* 1 if ts_step covers (size, n_tiles): 1 <= size <= 16, 0 <= n_tiles <= 32, else 0 */
 int ts_supported(int size, int n_tiles);
 
 /* ---------------------------------------------------------------------------------------

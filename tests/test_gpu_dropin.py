@@ -157,17 +157,28 @@ def test_degenerate_boards_like_the_reference(ts, golden_misc):
 
 
 def test_constructor_accepts_what_the_reference_accepts(ts):
-    """tests/test_state.py:614-642 of the reference only construct a 20x20 board and a 20-tile
-    board and read attributes; construction is lazy here, so that works, and the limits of the
-    kernels (S <= 16, T <= 8) surface as ValueError on first use."""
+    """tests/test_state.py:614-642 of the reference construct a 20x20 board and a 20-tile board and
+    only read attributes; construction is lazy here.  The 20-tile board also COMPUTES (tile counts up
+    to 32 go through the per-env kernels): observation and moves equal the oracle's.  The 20x20
+    board is beyond the kernels (S <= 16): ValueError on first use, never a host computation."""
     big = ts.GameState(20, [(10, 10)], [(0, 0)], [(19, 19)], False)
     assert big.size == 20 and big.is_blocked.shape == (20, 20) and big.is_blocked[10, 10]
-    many = ts.GameState(10, [], [(i // 10, i % 10) for i in range(20)], [(9 - i // 10, 9 - i % 10) for i in range(20)], False)
-    assert len(many.current_locations) == 20
     with pytest.raises(ValueError):
         big.move(ts.Move.UP)
-    with pytest.raises(ValueError):
-        many.get_state_array()
+    size, num_tiles = 10, 20
+    initial = [(i // size, i % size) for i in range(num_tiles)]
+    target = [(size - 1 - i // size, size - 1 - i % size) for i in range(num_tiles)]
+    for multi in (False, True):
+        many = ts.GameState(size, [], initial, target, multi)
+        want = orc.OracleState(size, [], initial, target, multi)
+        assert len(many.current_locations) == num_tiles
+        assert np.array_equal(many.get_state_array(), want.get_state_array())
+        for mv in "DRULDDLU":
+            assert many.move(ts.Move.from_char(mv)) == want.move(MOVES[mv])
+            assert [tuple(map(int, x)) for x in many.current_locations] == want.current_locations
+            assert many.is_won() == want.is_won()
+            assert [m.value for m in many.valid_moves()] == want.valid_moves()
+        assert np.array_equal(many.get_state_array(), want.get_state_array())
 
 
 def test_factory(ts, golden_misc):

@@ -104,6 +104,12 @@ SHAPES = [  # S, T, W, multi, N, K, max_steps
     (5, 2, 3, True, 1021, 300, 255),       # widest 1-byte step counter; N not a multiple of 4
     (5, 2, 3, False, 1023, 300, 256),      # first 4-byte step counter
     (6, 4, 8, True, 777, 40, 1),           # every step times out
+    (10, 20, 12, False, 1024, 48, 100),    # more than 8 tiles: the per-env generic kernels (the reference's own 20-tile board shape)
+    (16, 32, 50, True, 512, 40, 300),
+    (6, 12, 6, True, 1021, 64, 20),
+    (8, 9, 10, False, 515, 48, 100),
+    (12, 16, 20, True, 512, 40, 100),
+    (3, 9, 0, True, 256, 16, 9),           # a full board: nothing can ever move
 ]
 
 
@@ -198,13 +204,14 @@ def test_degenerate_batches_vs_oracle(ts, S, T, NT, W, multi, max_steps, auto_re
 
 
 def test_limits_are_value_errors_not_fallbacks(ts):
-    """More than 8 tiles / boards above 16x16 / more than 8 ordered targets on a mismatched board
+    """More than 32 tiles / boards above 16x16 / more than 32 ordered targets on a mismatched board
     are outside the kernels' domain: ValueError, never a host computation."""
     blocked = np.zeros((1, 9), np.uint8)
+    blocked = np.zeros((1, 49), np.uint8)
     with pytest.raises(ValueError):
-        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, np.zeros((1, 9, 2), np.uint8), np.zeros((1, 9, 2), np.uint8), True)
+        ts.BatchedTilerSliderEnv.from_arrays(7, blocked, np.zeros((1, 33, 2), np.uint8), np.zeros((1, 33, 2), np.uint8), True)
     with pytest.raises(ValueError):
-        ts.BatchedTilerSliderEnv.from_arrays(3, blocked, np.zeros((1, 1, 2), np.uint8), np.zeros((1, 9, 2), np.uint8), True)
+        ts.BatchedTilerSliderEnv.from_arrays(7, blocked, np.zeros((1, 1, 2), np.uint8), np.zeros((1, 33, 2), np.uint8), True)
     with pytest.raises(ValueError):
         ts.BatchedTilerSliderEnv(17, 1, 4)
 
@@ -296,7 +303,8 @@ def test_observation_valid_moves_goal(ts):
     rng = np.random.default_rng(11)
     for S, T, W, multi in [(5, 1, 5, False), (6, 4, 8, True), (6, 4, 8, False), (4, 2, 2, True), (8, 8, 10, True),
                            (12, 8, 36, True), (12, 8, 36, False), (16, 3, 50, False), (9, 5, 20, False),
-                           (11, 2, 30, True), (14, 8, 40, False), (15, 4, 60, True)]:
+                           (11, 2, 30, True), (14, 8, 40, False), (15, 4, 60, True), (10, 20, 12, False), (12, 16, 30, True),
+                           (6, 9, 5, True)]:
         N, K = 256, 12
         blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
         actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
@@ -621,7 +629,7 @@ def test_baseline_configs_at_their_literal_sizes(ts, S, T, W, multi, N, seed):
 
 
 def test_fuzz_random_shapes_vs_oracle(ts):
-    """Seeded fuzz over the whole shape space the kernels cover: board size 1..16, 0..8 tiles, target
+    """Seeded fuzz over the whole shape space the kernels cover: board size 1..16, 0..32 tiles, target
     counts equal to / different from the tile count, duplicate targets, both colour modes, auto-reset
     on / off, step limits around the counter-width boundaries, batch sizes that are not multiples of
     4 -- every field of every step against the oracle."""
@@ -629,10 +637,10 @@ def test_fuzz_random_shapes_vs_oracle(ts):
     n_cases = 0
     for case in range(70):
         S = int(rng.integers(1, 17))
-        T = int(rng.integers(0, min(8, S * S) + 1))
+        T = int(rng.integers(0, min(8, S * S) + 1)) if rng.random() < 0.75 else int(rng.integers(9, 33)) if S * S >= 32 else int(rng.integers(0, S * S + 1))
         W = int(rng.integers(0, max(1, (S * S - T) // 2) + 1)) if S * S - T > 0 else 0
         multi = bool(rng.integers(0, 2))
-        NT = T if rng.random() < 0.6 else int(rng.integers(0, min(8, S * S) + 1))
+        NT = T if rng.random() < 0.6 else int(rng.integers(0, min(32, S * S) + 1))
         auto_reset = bool(rng.integers(0, 2))
         max_steps = int(rng.choice([1, 2, 5, 17, 100, 254, 255, 256, 300]))
         N, K = int(rng.integers(1, 700)), int(rng.integers(4, 40))

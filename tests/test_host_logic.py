@@ -43,7 +43,8 @@ def test_layout_arithmetic():
         assert sum(widths) == nb and widths == sorted(widths, reverse=True)
         assert all(w in (1, 2, 4, 8, 16) for w in widths)
         assert [lib.ts_plane_offset(nb, k) for k in range(len(widths))] == [sum(widths[:k]) for k in range(len(widths))]
-    assert lib.ts_supported(6, 4) == 1 and lib.ts_supported(17, 1) == 0 and lib.ts_supported(6, 9) == 0
+    assert lib.ts_supported(6, 4) == 1 and lib.ts_supported(17, 1) == 0 and lib.ts_supported(6, 9) == 1 and lib.ts_supported(6, 33) == 0
+    assert [lib.ts_pos_bytes(t) for t in (0, 9, 16, 17, 32)] == [1, 16, 16, 32, 32]
 
 
 def test_argument_validation_without_gpu():
@@ -106,7 +107,7 @@ def test_validation_rejects_ill_formed():
     Puzzle(3, [(0, 0)], [(1, 1)], [(1, 1)]).validate()
     for bad in [Puzzle(3, [], [(0, 0), (0, 0)], [(1, 1), (2, 2)]), Puzzle(3, [(1, 1)], [(1, 1)], [(0, 0)]),
                 Puzzle(3, [], [(3, 0)], [(0, 0)]), Puzzle(17, [], [(0, 0)], [(1, 1)]),
-                Puzzle(4, [], [(0, i % 4) if i < 4 else (1, i % 4) for i in range(8)] + [(2, 0)], [])]:
+                Puzzle(6, [], [(i // 6, i % 6) for i in range(33)], [])]:      # 33 tiles: one more than the kernels cover
         with pytest.raises(ValueError):
             bad.validate()
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 CAP_ALIGN = 128
 MAX_SIZE = 16
-MAX_TILES = 8
+MAX_TILES = 32        # 0..8: register kernels; 9..32: per-env generic kernels
 F_DONE, F_WON, F_INVALID, F_TIMEOUT, F_STALE = 1, 2, 4, 8, 16
 GOAL_ORDERED, GOAL_SET = 0, 1
 

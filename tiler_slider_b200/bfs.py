@@ -66,8 +66,8 @@ class CudaBfsKernels:
     WON_CAPACITY = 1 << 16
 
     def __init__(self, table: BatchedTilerSliderEnv):
-        if table.size > 8:
-            raise ValueError("BFS supports board sizes up to 8")
+        if table.size > 8 or not 1 <= table.n_tiles <= 8:
+            raise ValueError("BFS supports board sizes up to 8 with 1 to 8 tiles")
         if table.n_tiles > 4 and table.n_envs > 1:
             raise ValueError("more than 4 tiles: the key has no room for a puzzle id, solve one puzzle at a time")
         self.t, self.lib, self.device = table, lib(), table.device

@@ -23,7 +23,8 @@ cudaError_t wide_step_dispatch(const ts_step_args&, cudaStream_t);
 cudaError_t wide_valid_dispatch(const ts_valid_args&, cudaStream_t);
 cudaError_t wide_goal_dispatch(const ts_goal_args&, cudaStream_t);
 cudaError_t generic_step_dispatch(const ts_step_args&, cudaStream_t);
-cudaError_t empty_goal_dispatch(const ts_goal_args&, cudaStream_t);
+cudaError_t generic_goal_dispatch(const ts_goal_args&, cudaStream_t);
+cudaError_t generic_valid_dispatch(const ts_valid_args&, cudaStream_t);
 
 static thread_local char g_err[256] = "ok";
 static int fail(int code, const char* fmt, ...) {
@@ -42,7 +43,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 static int check_shape(int size, int n_tiles, int64_t first, int64_t n, int64_t cap) {
     if (size < 1 || size > MAX_SIZE) return fail(TS_E_BAD_SIZE, "size %d outside 1..%d", size, MAX_SIZE);
-    if (n_tiles < 0 || n_tiles > MAX_TILES) return fail(TS_E_BAD_TILES, "n_tiles %d outside 0..%d", n_tiles, MAX_TILES);
+    if (n_tiles < 0 || n_tiles > MAX_TILES_ANY) return fail(TS_E_BAD_TILES, "n_tiles %d outside 0..%d", n_tiles, MAX_TILES_ANY);
     if (cap >= (int64_t)1 << 33) return fail(TS_E_BAD_CAPACITY, "capacity %lld too large (max 2^33 - 128 envs per call)", (long long)cap);
     if (cap <= 0 || cap % CAP_ALIGN != 0) return fail(TS_E_BAD_CAPACITY, "capacity %lld is not a positive multiple of %d", (long long)cap, CAP_ALIGN);
     if (first < 0 || n < 0 || first % GROUP != 0 || first + n > cap)
@@ -183,7 +184,7 @@ __global__ void synth_kernel(const ts_synth_args a) {
             a.d_targets_packed[env * pw + t] = v;
         }
     } else {
-        int tcells[MAX_TILES];
+        int tcells[MAX_TILES_ANY];
         for (int t = 0; t < T; ++t) tcells[t] = perm[W + T + t];
         store_target_board(a.d_targets_packed, cap, env, S, T, tcells, T);
     }
@@ -206,7 +207,7 @@ int ts_plane_width(int n_bytes, int k) { return plane_width(n_bytes, k); }
 int ts_plane_offset(int n_bytes, int k) { return plane_offset(n_bytes, k); }
 int ts_walls_bytes(int size) { return walls_bytes(size); }
 int ts_target_board_bytes(int size) { return target_board_bytes(size); }
-int ts_supported(int size, int n_tiles) { return size >= 1 && size <= MAX_SIZE && n_tiles >= 0 && n_tiles <= MAX_TILES; }
+int ts_supported(int size, int n_tiles) { return size >= 1 && size <= MAX_SIZE && n_tiles >= 0 && n_tiles <= MAX_TILES_ANY; }
 
 int ts_encode(const ts_encode_args* a, void* stream) {
     if (!a) return fail(TS_E_NULL_POINTER, "null args");
@@ -254,7 +255,8 @@ int ts_step(const ts_step_args* a, void* stream) {
     ts_step_args args = *a;
     if (args.max_steps < 1) args.max_steps = 1;   // step_count >= max_steps holds on the first step either way
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->n_tiles == 0) return cuda_result(generic_step_dispatch(args, st), "ts_step launch");   // nothing to slide (ts_generic.cu)
+    if (a->n_tiles == 0 || a->n_tiles > MAX_TILES)      // nothing to slide / more tiles than the register kernels hold (ts_generic.cu)
+        return cuda_result(generic_step_dispatch(args, st), "ts_step launch");
     // the bitboard kernels own whole 4-env groups: the ragged end of the range goes to the generic kernel
     const int64_t ragged = wide_board(a->size) ? 0 : a->n_envs % GROUP;
     args.n_envs -= ragged;
@@ -299,6 +301,7 @@ int ts_valid_moves(const ts_valid_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->n_tiles == 0)      // no tile, no move that changes anything
         return cuda_result(cudaMemsetAsync(a->d_mask + a->first_env, 0, (size_t)a->n_envs, st), "ts_valid_moves memset");
+    if (a->n_tiles > MAX_TILES) return cuda_result(generic_valid_dispatch(*a, st), "ts_valid_moves launch");
     switch (a->size) {
         case 1: e = valid_dispatch_s1(*a, st); break;
         case 2: e = valid_dispatch_s2(*a, st); break;
@@ -322,7 +325,7 @@ int ts_goal_check(const ts_goal_args* a, void* stream) {
     if (a->n_envs == 0) return 0;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->n_tiles == 0) return cuda_result(empty_goal_dispatch(*a, st), "ts_goal_check launch");
+    if (a->n_tiles == 0 || a->n_tiles > MAX_TILES) return cuda_result(generic_goal_dispatch(*a, st), "ts_goal_check launch");
     switch (a->size) {
         case 1: e = goal_dispatch_s1(*a, st); break;
         case 2: e = goal_dispatch_s2(*a, st); break;

@@ -35,9 +35,10 @@ namespace ts {
 constexpr int GROUP = 4;           // envs per thread
 constexpr int CAP_ALIGN = 128;     // capacity granularity (envs)
 constexpr int MAX_SIZE = 16;
-constexpr int MAX_TILES = 8;
+constexpr int MAX_TILES = 8;        // tile counts the register kernels are instantiated for
+constexpr int MAX_TILES_ANY = 32;   // tile counts the library covers (9..32: per-env generic kernels, ts_generic.cu)
 
-__host__ __device__ constexpr int pos_bytes(int T) { return T <= 1 ? 1 : T <= 2 ? 2 : T <= 4 ? 4 : 8; }   // T = 0: one (zero) byte
+__host__ __device__ constexpr int pos_bytes(int T) { return T <= 1 ? 1 : T <= 2 ? 2 : T <= 4 ? 4 : T <= 8 ? 8 : T <= 16 ? 16 : 32; }   // T = 0: one (zero) byte
 __host__ __device__ constexpr bool padded_board(int S) { return S <= 6; }
 __host__ __device__ constexpr int board_stride(int S) { return padded_board(S) ? S + 1 : S; }
 __host__ __device__ constexpr int pos_stride(int S) { return padded_board(S) ? S + 1 : 16; }

@@ -10,7 +10,7 @@ through the C-ABI.  Only the Python exceptions of step() (RuntimeError after don
 TypeError on a non-enum action; environment.py:113-117) and the info dict are assembled on
 the host, from the flag byte the step kernel returns.
 
-Limits (ValueError): board size <= 16, 0..8 tiles, well-formed puzzles only (distinct tiles,
+Limits (ValueError): board size <= 16, 0..32 tiles, well-formed puzzles only (distinct tiles,
 none on a blocked cell; outside that domain the reference itself is erratic).
 Boards without tiles (won iff there are no targets either) and multi-colour boards whose target
 count differs from their tile count (they play normally and never win, state.py:183-184) behave
