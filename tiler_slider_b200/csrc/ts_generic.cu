@@ -26,6 +26,11 @@ __device__ __forceinline__ uint64_t load_board64(const uint8_t* base, int S, siz
     for (int k = 0; k < nb; ++k) b |= (uint64_t)base[board_byte_addr(nb, cap, env, k)] << (8 * k);
     return b;
 }
+__device__ __forceinline__ uint64_t cell_mask64(int S) {
+    uint64_t m = 0;
+    for (int r = 0; r < S; ++r) m |= (uint64_t)((1u << S) - 1u) << (r * board_stride(S));
+    return m;
+}
 // rows[r] = row r of env's WALL board, cell (r, c) at bit c -- every board class
 __device__ __forceinline__ void wall_rows(uint32_t* rows, const uint8_t* d_walls, int S, size_t cap, size_t env) {
     const uint32_t cells = (1u << S) - 1u;
@@ -58,6 +63,12 @@ __device__ __forceinline__ bool goal_met(const uint8_t* p, int S, int T, int goa
             if (p[t] != d_targets[env * pw + t]) return false;
         return true;
     }
+    if (!wide_board(S)) {                       // occupancy == target bitboard, both in one word
+        const int bs = board_stride(S);
+        uint64_t occ = 0;
+        for (int t = 0; t < T; ++t) occ |= 1ull << ((p[t] / ps) * bs + p[t] % ps);
+        return occ == (load_board64(d_targets, S, cap, env) & cell_mask64(S));
+    }
     uint32_t occ[MAX_SIZE], tgt[MAX_SIZE];
     target_rows(tgt, d_targets, S, cap, env);
     for (int r = 0; r < S; ++r) occ[r] = 0;
@@ -78,7 +89,23 @@ __global__ void __launch_bounds__(128) generic_step_kernel(const ts_step_args a)
     uint8_t p0[MAX_TILES_ANY], p[MAX_TILES_ANY];
     for (int t = 0; t < T; ++t) p[t] = p0[t] = a.d_pos[env * pw + t];
     bool moved = false;
-    if (T > 0) {
+    if (T > 0 && !wide_board(S)) {             // the whole board in one word: register bit tests (ragged ends, the single-env adapter)
+        const int bs = board_stride(S);
+        const uint64_t walls = load_board64(a.d_walls, S, cap, env);
+        uint64_t occ = 0;
+        for (int t = 0; t < T; ++t) occ |= 1ull << ((p0[t] / ps) * bs + p0[t] % ps);
+        for (int t = 0; t < T; ++t) {
+            const int r = p0[t] / ps, c = p0[t] % ps;
+            int n = 0;
+            for (int rr = r + dr, cc = c + dc; rr >= 0 && rr < S && cc >= 0 && cc < S; rr += dr, cc += dc) {
+                const int bit = rr * bs + cc;
+                if ((walls >> bit) & 1ull) break;
+                if (!((occ >> bit) & 1ull)) ++n;
+            }
+            p[t] = (uint8_t)((r + n * dr) * ps + (c + n * dc));
+            moved |= n != 0;
+        }
+    } else if (T > 0) {                        // wide boards with more than 8 tiles: row words in local arrays
         uint32_t walls[MAX_SIZE], occ[MAX_SIZE];
         wall_rows(walls, a.d_walls, S, cap, env);
         for (int r = 0; r < S; ++r) occ[r] = 0;
