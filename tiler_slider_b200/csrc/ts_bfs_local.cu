@@ -32,7 +32,10 @@
 
 namespace ts {
 
-constexpr int LOCAL_THREADS = 256;
+#ifndef TS_LOCAL_THREADS
+#define TS_LOCAL_THREADS 256
+#endif
+constexpr int LOCAL_THREADS = TS_LOCAL_THREADS;
 constexpr int LOCAL_HIST = 256;          // levels a puzzle may have here (a deeper one is left to the hash-partitioned search)
 
 template <int T> __device__ __forceinline__ void sort_bytes4(uint32_t& q) {
