@@ -657,3 +657,33 @@ def test_fuzz_random_shapes_vs_oracle(ts):
         assert_same(got, want, f"fuzz case {case}: S{S} T{T} NT{NT} W{W} multi{multi} ar{auto_reset} ms{max_steps} N{N}")
         n_cases += 1
     assert n_cases == 70
+
+
+@pytest.mark.parametrize("S,T,W,multi", [(6, 4, 8, True), (12, 8, 36, True), (5, 1, 5, False), (8, 5, 14, False)])
+def test_long_rollout_with_many_resets(ts, S, T, W, multi):
+    """2,000 steps of 2,048 envs with auto-reset (about 20 episodes per env at max_steps = 100, more
+    where boards are won): final positions, final step counters and the per-step flag / reward
+    checksums must equal the oracle's -- no drift over resets, counters or the fast path."""
+    N, K = 2048, 2000
+    rng = np.random.default_rng(S * 7 + T)
+    blocked, tiles, targets = random_puzzles(rng, N, S, T, W)
+    actions = rng.integers(0, 4, size=(K, N), dtype=np.uint8)
+    want = orc.rollout(S, multi, blocked, tiles, targets, actions, max_steps=100, auto_reset=True)
+    env = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=100, auto_reset=True)
+    fast = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi, max_steps=100, auto_reset=True, track_flags=False)
+    acts = torch.zeros(K, env.capacity, dtype=torch.uint8, device="cuda")
+    acts[:, :N] = torch.as_tensor(actions).cuda()
+    flag_sum = torch.zeros(N, dtype=torch.int64, device="cuda")
+    rew_sum = torch.zeros(N, dtype=torch.float64, device="cuda")
+    for k in range(K):
+        _, r, _ = env.step(acts[k])
+        fast.step(acts[k])
+        flag_sum += env.flags.to(torch.int64) * (k % 251 + 1)
+        rew_sum += r.to(torch.float64)
+    assert np.array_equal(env.positions().cpu().numpy(), want["final_pos"])
+    assert np.array_equal(env.step_count.to(torch.int32).cpu().numpy(), want["final_count"])
+    w = (want["flags"].astype(np.int64) * (np.arange(K) % 251 + 1)[:, None]).sum(0)
+    assert np.array_equal(flag_sum.cpu().numpy(), w)
+    assert np.array_equal(rew_sum.cpu().numpy(), want["reward"].astype(np.float64).sum(0))
+    assert torch.equal(fast.pos, env.pos) and torch.equal(fast.step_count, env.step_count)
+    assert (want["flags"] & F_DONE).sum() > 15 * N
