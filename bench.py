@@ -488,6 +488,12 @@ class Runner:
             "value": res.generated / warm, "seconds": warm, "seconds_cold": cold, "unique_states": res.n_states,
             "generated_successors": res.generated, "depth": len(res.levels) - 1, "table_log2_per_rank": log2,
             "exchange": (solver.exchange if self.world > 1 else "none (one rank)"),
+            # keys that crossed NVLink: 8 bytes each, (G-1)/G of the keys a rank sends have a remote owner
+            "nvlink": ({"keys_exchanged": res.exchanged_keys,
+                        "bytes_per_gpu_per_direction": 8 * res.exchanged_keys * (self.world - 1) / self.world / self.world,
+                        "GBps_per_gpu_per_direction": 8 * res.exchanged_keys * (self.world - 1) / self.world / self.world / warm / 1e9,
+                        "of_measured_peer_copy_770_GBps": 8 * res.exchanged_keys * (self.world - 1) / self.world / self.world / warm / 1e9 / 770.0}
+                       if self.world > 1 and res.exchanged_keys else None),
             "roofline": {"bound": "hbm", "achieved": 42 * res.generated / self.world / warm / 1e9, "peak": self.peak, "unit": "GB/s",
                          "frac": 42 * res.generated / self.world / warm / 1e9 / self.peak, "traffic": None,
                          "kernel": "ts::bfs_hash_insert_kernel (K5) + bfs_expand(_exchange)_kernel (K4/K4x)",

@@ -49,6 +49,7 @@ class BfsResult:
     per_level_seconds: list[float] = field(default_factory=list)
     solutions: list[str | None] | None = None  # with_paths: a shortest move string per puzzle ('UDLR'), None if unsolved
     fallback_puzzles: int = 0                  # LocalBfs: puzzles that did not fit on chip and went through the hash-partitioned search
+    exchanged_keys: int = 0                    # hash-partitioned search over several ranks: keys sent to their owners (all ranks, all levels)
 
 
 @dataclass
@@ -395,7 +396,8 @@ class BfsSolver:
             dist.all_reduce(depth_pp, op=dist.ReduceOp.MIN, group=self.group)
             depth_pp = torch.where(depth_pp >= (1 << 30), torch.full_like(depth_pp, -1), depth_pp)
         return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
-                         solve_depth_per_puzzle=depth_pp, generated=generated)
+                         solve_depth_per_puzzle=depth_pp, generated=generated,
+                         exchanged_keys=int(sum(x[3] for x in (xrows or []))))
 
     LEVELS_PER_SYNC = 16        # device-driven search: levels launched between two host read-backs
     BIG_LEVEL = 1 << 19         # frontiers from this size on get their own launch geometry and read-back
