@@ -622,7 +622,7 @@ class CudaLocalKernels:
             got, n_sm = C.c_int(0), C.c_int(0)
             with torch.cuda.device(self.device):
                 rc = self.lib.ts_bfs_local_ctas_per_sm(C.byref(a), C.byref(got), C.byref(n_sm))
-            if rc == 0 and got.value >= 1:
+            if rc == 0 and got.value >= (k if self.want_ctas is None else 1):
                 grid = got.value * n_sm.value
                 spill = int(min(bits + 1, self.MAX_SCRATCH_BYTES // 4 // grid))
                 plan = dict(bitmap_words=bitmap_bytes // 4, queue_smem=queue, grid=grid, ctas_per_sm=got.value,
