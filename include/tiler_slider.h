@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define TS_VERSION 200          /* 0.2.0 */
+#define TS_VERSION 201          /* 0.2.1 */
 #define TS_CAP_ALIGN 128
 #define TS_MAX_SIZE 16
 #define TS_MAX_TILES 32         /* 0..8: register kernels; 9..32: per-env generic kernels (csrc/ts_generic.cu) */
@@ -247,20 +247,25 @@ int ts_goal_check(const ts_goal_args *a, void *stream);
 #define TS_BFS_NONE 0xFFFFFFFFFFFFFFFFull
 #define TS_BFS_WON_BIT 0x8000000000000000ull
 typedef struct ts_bfs_args {
-    int32_t size, n_tiles, goal_mode, never_win, n_ranks, reserved;
+    int32_t size, n_tiles, goal_mode, never_win, n_ranks;
+    int32_t rank;                       /* ts_bfs_trace_step: the caller's rank among n_ranks owners */
     int64_t n_items, puzzle_capacity, table_capacity, out_capacity;
     const uint8_t *d_walls, *d_targets_packed, *d_init;
     const uint64_t *d_in_keys;
     uint64_t *d_out_keys, *d_table, *d_counts;
-    /* optional parent tracking (single-rank searches): with d_table_parent given,
-     * ts_bfs_hash_insert records for every new key the key it was expanded from --
-     * d_in_keys[i] must then be exactly the output of ts_bfs_expand on d_parent_keys, so that
-     * the parent of d_in_keys[i] is d_parent_keys[i / 4]; d_parent_keys = NULL marks roots */
+    /* optional parent tracking: with d_table_parent given, ts_bfs_hash_insert records for every
+     * new key the key it was expanded from; d_parent_keys = NULL marks roots.
+     *   parent_per_item = 0 (single rank): d_in_keys must be exactly the output of ts_bfs_expand
+     *     on d_parent_keys, so that the parent of d_in_keys[i] is d_parent_keys[i / 4];
+     *   parent_per_item = 1 (several ranks): the parent of d_in_keys[i] is d_parent_keys[i] --
+     *     the array ts_bfs_partition_scatter filled next to the keys (d_out_parents) and the
+     *     caller exchanged with them. */
     const uint64_t *d_parent_keys;
     uint64_t *d_table_parent;
-    /* ts_bfs_traceback: d_in_keys[i] = goal state of item i (TS_BFS_NONE: none); writes the
-     * shortest move string of item i to d_moves[i * max_moves ...] (0..3, root first) and its
-     * length to d_lengths[i] (-1: no goal / longer than max_moves / broken chain) */
+    /* ts_bfs_traceback: d_in_keys[i] = goal state of item i (TS_BFS_NONE: none), d_parent_keys[i]
+     * = the state it was generated from (d_goal_parents of the inserts); writes the shortest move
+     * string of item i to d_moves[i * max_moves ...] (0..3, root first) and its length to
+     * d_lengths[i] (-1: no goal / longer than max_moves / broken chain) */
     uint8_t *d_moves;
     int32_t *d_lengths;
     int64_t max_moves;
@@ -285,7 +290,7 @@ typedef struct ts_bfs_args {
      * (hash(key) % n_ranks); d_counts[3] += number of keys sent. */
     uint64_t *const *d_peer_bufs;
     int64_t inbox_capacity;
-    int32_t parity, reserved3;
+    int32_t parity, parent_per_item;
     /* device-driven levels (ts_bfs_expand, ts_bfs_hash_insert), optional: the item count is read
      * on the DEVICE as min(n_items, *d_n_items * n_items_scale) -- n_items is then only the
      * bound the grid is sized for -- so consecutive levels can be launched back to back
@@ -294,6 +299,16 @@ typedef struct ts_bfs_args {
      * the counter block of level d+1. */
     const int64_t *d_n_items;
     int64_t n_items_scale;
+    /* ts_bfs_partition_scatter, optional (with d_parent_keys = the frontier d_in_keys was expanded
+     * from): d_out_parents[j] = parent of the key written to d_out_keys[j] */
+    uint64_t *d_out_parents;
+    /* ts_bfs_hash_insert, optional (with d_goal_keys and d_parent_keys): d_goal_parents[pid] = the
+     * state the goal successor stored in d_goal_keys[pid] was generated from.  A shortest solution
+     * is the chain root -> that state plus the move from it to the goal; the goal state's own
+     * table entry must not be used for this, because a puzzle whose initial state already meets
+     * the goal is won by its first step (a root is never a goal successor), and the root has no
+     * parent. */
+    uint64_t *d_goal_parents;
 } ts_bfs_args;
 #define TS_BFS_XHDR 16
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
@@ -306,6 +321,16 @@ int ts_bfs_hash_insert(const ts_bfs_args *a, void *stream);
  * of the sent counts doubles as the termination test) and alternates `parity` level by level. */
 int ts_bfs_expand_exchange(const ts_bfs_args *a, void *stream);
 int ts_bfs_traceback(const ts_bfs_args *a, void *stream);
+/* One step of a traceback over a visited set that is spread over n_ranks owners (hash-partitioned
+ * search with parents): for every item i whose key d_in_keys[i] this rank owns, look the key up and
+ * write its parent to d_out_keys[i] and the move that leads from the parent to it to d_moves[i]
+ * (one byte per item).  Read as int64: parent >= 0; -1 (TS_BFS_NONE) the key is a root; -2 the chain
+ * is broken (key or move not found); INT64_MIN (with move 0) for TS_BFS_NONE items and for keys of
+ * other ranks -- so a MAX all-reduce of both arrays over the owners yields the step for every
+ * item.  n_ranks = 1: every key is this rank's.  With d_parent_keys given (the last link of a
+ * solution, d_goal_parents) nothing is looked up: the parent of item i is d_parent_keys[i], on
+ * every rank. */
+int ts_bfs_trace_step(const ts_bfs_args *a, void *stream);
 /* n_levels device-driven BFS levels launched back to back (2 kernels per level, no host sync):
  * level d = first_depth .. first_depth + n_levels - 1 expands the lvl[4*d] keys of
  * front[d & 1] into succ (4 * frontier_capacity keys) and inserts them as level d+1 into

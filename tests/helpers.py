@@ -29,3 +29,16 @@ def random_puzzles(rng, n, S, T, W):
     tiles = np.stack([tcell // S, tcell % S], axis=-1).astype(np.uint8)
     targets = np.stack([gcell // S, gcell % S], axis=-1).astype(np.uint8)
     return blocked, tiles, targets
+
+
+def reachable_targets(orc, rng, S, blocked, tiles, multi, n_moves):
+    """targets = where the tiles stand after n_moves random moves (oracle), so that every puzzle of the
+    batch has a solution"""
+    out = np.zeros_like(tiles)
+    for e in range(tiles.shape[0]):
+        bl = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+        st = orc.OracleState(S, bl, tiles[e].tolist(), tiles[e].tolist(), multi)
+        for m in rng.integers(0, 4, n_moves):
+            st.move(int(m))
+        out[e] = np.array(st.current_locations, dtype=tiles.dtype)
+    return out

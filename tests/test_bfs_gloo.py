@@ -49,37 +49,90 @@ class OracleBfsKernels:
                 out.append(-1 if (k & ~(-(1 << 63))) == key and not won else k)
         return torch.tensor(out, dtype=torch.int64)
 
-    def partition(self, keys, n_ranks):
-        ks = [k for k in keys.tolist() if k != -1]
-        owner = [((k & 0x7FFFFFFFFFFFFFFF) * 2654435761 >> 7) % n_ranks for k in ks]
-        order = sorted(range(len(ks)), key=lambda i: owner[i])
-        return torch.tensor([ks[i] for i in order], dtype=torch.int64), [owner.count(r) for r in range(n_ranks)]
+    @staticmethod
+    def _owner(k, n_ranks):
+        return ((k & 0x7FFFFFFFFFFFFFFF) * 2654435761 >> 7) % n_ranks
+
+    def partition(self, keys, n_ranks, parents=None):
+        """(bucketed keys, sizes, bucketed parents or None): parents = the frontier `keys` was expanded from"""
+        items = [(k, i) for i, k in enumerate(keys.tolist()) if k != -1]
+        owner = [self._owner(k, n_ranks) for k, _ in items]
+        order = sorted(range(len(items)), key=lambda j: owner[j])
+        par = None
+        if parents is not None:
+            pl = parents.tolist()
+            par = torch.tensor([pl[items[j][1] // 4] & 0x7FFFFFFFFFFFFFFF for j in order], dtype=torch.int64)
+        return torch.tensor([items[j][0] for j in order], dtype=torch.int64), [owner.count(r) for r in range(n_ranks)], par
 
     def new_table(self, capacity):
-        return set()
+        return {}
 
-    def insert(self, table, keys):
+    def insert(self, table, keys, parents=None, parent_table=None, stats=None, parent_per_item=False):
+        """table: key -> True; parent_table (a second dict): key -> parent key (-1 for roots)"""
         new, n_won = [], 0
-        for raw in keys.tolist():
+        pl = None if parents is None else parents.tolist()
+        for i, raw in enumerate(keys.tolist()):
             if raw == -1:
                 continue
             n_won += raw < 0
             k = raw & 0x7FFFFFFFFFFFFFFF
             if k not in table:
-                table.add(k)
+                table[k] = True
+                if parent_table is not None:
+                    parent_table[k] = -1 if pl is None else pl[i if parent_per_item else i // 4] & 0x7FFFFFFFFFFFFFFF
                 new.append(raw)
         return torch.tensor(new, dtype=torch.int64), n_won
 
+    def _move_between(self, parent, key):
+        succ = self.expand(torch.tensor([parent], dtype=torch.int64)).tolist()
+        for d in range(4):
+            if succ[d] != -1 and succ[d] & 0x7FFFFFFFFFFFFFFF == key:
+                return d
+        return -1
 
-def _worker(rank, world, port, puzzles, q):
+    def traceback(self, table, parent_table, goals, max_moves):
+        """goals = int64[2, n]: goal successor, the state it was generated from"""
+        n = goals.shape[1]
+        moves, lengths = torch.zeros(n, max_moves, dtype=torch.uint8), torch.full((n,), -1, dtype=torch.int32)
+        for i, (g, frm) in enumerate(zip(*goals.tolist())):
+            if g == -1:
+                continue
+            k, path = frm & 0x7FFFFFFFFFFFFFFF, [self._move_between(frm & 0x7FFFFFFFFFFFFFFF, g & 0x7FFFFFFFFFFFFFFF)]
+            while parent_table[k] != -1:
+                path.append(self._move_between(parent_table[k], k))
+                k = parent_table[k]
+            lengths[i] = len(path)
+            moves[i, : len(path)] = torch.tensor(path[::-1], dtype=torch.uint8)
+        return moves, lengths
+
+    def trace_step(self, table, parent_table, keys, rank, n_ranks, given_parents=None):
+        """the contract of ts_bfs_trace_step (include/tiler_slider.h)"""
+        out = torch.zeros(2, keys.numel(), dtype=torch.int64)
+        for i, raw in enumerate(keys.tolist()):
+            k = raw & 0x7FFFFFFFFFFFFFFF
+            if raw != -1 and given_parents is not None:
+                out[0, i] = int(given_parents[i]) & 0x7FFFFFFFFFFFFFFF
+                out[1, i] = self._move_between(int(out[0, i]), k)
+            elif raw == -1 or (n_ranks > 1 and self._owner(k, n_ranks) != rank):
+                out[0, i] = -(1 << 63)
+            elif k not in parent_table:
+                out[0, i] = -2
+            else:
+                out[0, i] = parent_table[k]
+                if parent_table[k] != -1:
+                    out[1, i] = self._move_between(parent_table[k], k)
+        return out
+
+
+def _worker(rank, world, port, puzzles, q, with_paths=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tiler_slider_b200.bfs import BfsSolver
-    res = BfsSolver(kernels=OracleBfsKernels(puzzles), n_puzzles=len(puzzles), table_capacity=1 << 16).solve()
+    res = BfsSolver(kernels=OracleBfsKernels(puzzles), n_puzzles=len(puzzles), table_capacity=1 << 16).solve(with_paths=with_paths)
     if rank == 0:
         q.put((res.n_states, res.levels, res.solve_depth, res.states_per_puzzle.tolist(),
-               res.solve_depth_per_puzzle.tolist(), res.generated))
+               res.solve_depth_per_puzzle.tolist(), res.generated) + ((res.solutions,) if with_paths else ()))
     dist.destroy_process_group()
 
 
@@ -115,6 +168,45 @@ def test_bfs_driver_over_gloo(world):
     want = [(la[i] if i < len(la) else 0) + (lb[i] if i < len(lb) else 0) for i in range(max(len(la), len(lb)))]
     assert levels == want
     assert generated == 4 * n_states
+
+
+def _replay(puzzle, solution):
+    """does the move string take the puzzle from its initial state to the goal (oracle move)?"""
+    from oracle import oracle as orc
+    st = orc.OracleState(puzzle["size"], puzzle["blocked"], puzzle["tiles"], puzzle["targets"], puzzle["multi_color"])
+    won = False
+    for ch in solution:
+        won = st.move("UDLR".index(ch))
+    return won
+
+
+def test_bfs_shortest_paths_over_gloo():
+    """with_paths on two ranks: the parent of every key travels with it to the key's owner, and the
+    chains are walked one collective per move, each rank answering for the keys it owns.  The
+    strings must have the known optimal lengths and solve the puzzles when replayed; a one-rank
+    run of the same driver gives strings of the same lengths."""
+    gold = {b["name"]: b for b in _golden_bfs()}
+    # the fourth puzzle starts on its goal: it is won by its first step (the reference evaluates the
+    # goal inside step(), environment.py:133), so its shortest solution is one move, not none
+    on_goal = dict(size=6, blocked=[[3, 3]], tiles=[[0, 0], [0, 2], [0, 4]], targets=[[0, 0], [0, 2], [0, 4]], multi_color=True)
+    batch = [gold["puzzle_multi_111"], gold["puzzle_multi_180"], gold["puzzle_multi_111"], on_goal]
+    sys.path.insert(0, ROOT)
+    from tiler_slider_b200.bfs import BfsSolver
+    one = BfsSolver(kernels=OracleBfsKernels(batch), n_puzzles=4, table_capacity=1 << 16).solve(with_paths=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29539, batch, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[3] == one.states_per_puzzle.tolist() and got[3][:3] == [558, 950, 558]
+    assert got[4] == one.solve_depth_per_puzzle.tolist() == [8, 13, 8, 1]          # UP moves nothing and wins
+    for sols in (one.solutions, got[6]):
+        assert [len(s) for s in sols] == got[4]
+        assert all(_replay(p, s) for p, s in zip(batch, sols))
 
 
 def test_bfs_driver_argument_checks():

@@ -109,6 +109,40 @@ def test_shortest_solution_strings(ts, golden_misc):
         assert n_solved > 5
 
 
+@pytest.mark.parametrize("S,T,W,multi,n", [(5, 2, 4, True, 96), (6, 3, 9, False, 64), (4, 1, 2, False, 48)])
+def test_solutions_of_reachable_targets_and_boards_that_start_on_their_goal(ts, S, T, W, multi, n):
+    """Targets = where the tiles stand after a random walk, so every puzzle has a solution -- and a
+    few walks end where they began: such a board is won by its first step (the goal is evaluated
+    inside step(), environment.py:133), so its solution is one move (or a cycle), never the empty
+    string.  Depths equal the oracle's BFS; every string wins on its last move, not earlier; the
+    hash-partitioned search (device- and host-driven) and the on-chip search agree."""
+    from tiler_slider_b200.bfs import BfsSolver, LocalBfs
+    from tests.helpers import random_puzzles, reachable_targets
+    rng = np.random.default_rng(S * 10 + T)
+    blocked, tiles, _ = random_puzzles(rng, n, S, T, W)
+    targets = reachable_targets(orc, rng, S, blocked, tiles, multi, 9)
+    tiles[0] = targets[0]                                  # at least one board starts on its goal
+    table = ts.BatchedTilerSliderEnv.from_arrays(S, blocked, tiles, targets, multi)
+    want = []
+    for e in range(n):
+        bl = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+        want.append(orc.OracleState(S, bl, tiles[e].tolist(), targets[e].tolist(), multi).bfs(max_states=1 << 20)[2])
+    assert sum(d > 0 for d in want) > n // 2
+    on_goal = [e for e in range(n) if (tiles[e] == targets[e]).all()]
+    assert on_goal and all(want[e] != 0 for e in on_goal)
+    for res in (BfsSolver(table, table_capacity=1 << 20).solve(with_paths=True),
+                BfsSolver(table, table_capacity=1 << 20).solve(with_paths=True, device_driven=False),
+                LocalBfs(table).solve(with_paths=True)):
+        assert res.solve_depth_per_puzzle.tolist() == want
+        for e in range(n):
+            if want[e] < 0:
+                assert res.solutions[e] is None
+                continue
+            bl = [(c // S, c % S) for c in np.flatnonzero(blocked[e])]
+            assert len(res.solutions[e]) == want[e]
+            assert _replay((S, bl, tiles[e].tolist(), targets[e].tolist(), multi), res.solutions[e])[:1] == [want[e]]
+
+
 def test_more_than_four_tiles_single_puzzle(ts):
     from tiler_slider_b200.bfs import solve_puzzle
     p = ts.Puzzle(5, [(2, 2), (0, 3)], [(0, 0), (0, 1), (1, 0), (4, 4), (3, 3)], [(4, 0), (4, 1), (4, 2), (4, 3), (0, 4)], False)

@@ -37,3 +37,15 @@ def test_two_gpu_exchanges_match_single_gpu():
     assert local["oracle_check"]["ok"] and local["mode"] == "local"
     for key in ("unique_states", "generated_successors", "depth", "puzzles_solved", "max_solve_depth"):
         assert local[key] == one[key], ("local", key)
+
+
+def test_two_gpu_shortest_paths():
+    """with_paths over two ranks (parents exchanged with the keys, the chains walked one collective
+    per move): same strings lengths as a single-rank search, every string replayed through the CPU
+    oracle wins on its last move (tests/bfs_paths_multi_check.py)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join("tests", "bfs_paths_multi_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    rep = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rep["ok"] and len(rep["cases"]) == 6 and all(c["solved"] > 0 for c in rep["cases"])

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     lib = _lib.lib()
-    assert lib.ts_version() == 200
+    assert lib.ts_version() == 201
 
 
 def test_layout_arithmetic():

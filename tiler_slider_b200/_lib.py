@@ -69,7 +69,7 @@ class GoalArgs(C.Structure):
 
 class BfsArgs(C.Structure):
     _fields_ = [("size", _i32), ("n_tiles", _i32), ("goal_mode", _i32), ("never_win", _i32), ("n_ranks", _i32),
-                ("reserved", _i32),
+                ("rank", _i32),
                 ("n_items", _i64), ("puzzle_capacity", _i64), ("table_capacity", _i64), ("out_capacity", _i64),
                 ("d_walls", _vp), ("d_targets_packed", _vp), ("d_init", _vp), ("d_in_keys", _vp),
                 ("d_out_keys", _vp), ("d_table", _vp), ("d_counts", _vp),
@@ -77,8 +77,8 @@ class BfsArgs(C.Structure):
                 ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64),
                 ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_goal_keys", _vp),
                 ("depth", _i32), ("reserved2", _i32),
-                ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("reserved3", _i32),
-                ("d_n_items", _vp), ("n_items_scale", _i64)]
+                ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("parent_per_item", _i32),
+                ("d_n_items", _vp), ("n_items_scale", _i64), ("d_out_parents", _vp), ("d_goal_parents", _vp)]
 
 
 class BfsLocalArgs(C.Structure):
@@ -119,6 +119,7 @@ SYMBOLS = {
     "ts_bfs_partition_scatter": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_hash_insert": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_traceback": (C.c_int, [C.POINTER(BfsArgs), _vp]),
+    "ts_bfs_trace_step": (C.c_int, [C.POINTER(BfsArgs), _vp]),
     "ts_bfs_local_smem_bytes": (C.c_int, [C.POINTER(BfsLocalArgs)]),
     "ts_bfs_local_ctas_per_sm": (C.c_int, [C.POINTER(BfsLocalArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ts_bfs_local": (C.c_int, [C.POINTER(BfsLocalArgs), C.c_int, _vp]),

@@ -57,7 +57,7 @@ class BfsStats:
     """Per-puzzle tallies ts_bfs_hash_insert keeps on the device (CudaBfsKernels.insert(stats=...))."""
     states: torch.Tensor                       # int64[P]  += 1 per new key
     solve_depth: torch.Tensor                  # int32[P]  min over goal successors of `depth`
-    goal_keys: torch.Tensor | None             # int64[P]  a goal state at that depth (with_paths)
+    goal_keys: torch.Tensor | None             # int64[2, P]  with_paths: a goal successor at that depth, and the state it was generated from
     depth: int = 0                             # depth of the keys being inserted
 
 
@@ -117,18 +117,23 @@ class CudaBfsKernels:
                                                       d_out_keys=out.data_ptr()), "ts_bfs_expand")
         return out
 
-    def partition(self, keys: torch.Tensor, n_ranks: int) -> tuple[torch.Tensor, list[int]]:
-        """Bucket keys by owner rank (NONE dropped).  Returns (bucketed keys, bucket sizes)."""
+    def partition(self, keys: torch.Tensor, n_ranks: int, parents: torch.Tensor | None = None):
+        """Bucket keys by owner rank (NONE dropped).  Returns (bucketed keys, bucket sizes, bucketed
+        parents or None): with `parents` = the frontier `keys` was expanded from, the parent of
+        every key is written next to it, in the same order."""
         counts = torch.zeros(n_ranks, dtype=torch.int64, device=self.device)
         a = self._args(n_items=keys.numel(), n_ranks=n_ranks, d_in_keys=keys.data_ptr(), d_counts=counts.data_ptr())
         self._call(self.lib.ts_bfs_partition_count, a, "ts_bfs_partition_count")
         sizes = counts.tolist()                                    # host copy: the all-to-all needs split sizes
         cursor = torch.cumsum(counts, 0) - counts
         out = self.workspace("send", sum(sizes))
+        out_par = self.workspace("send_par", sum(sizes)) if parents is not None else None
         a = self._args(n_items=keys.numel(), n_ranks=n_ranks, d_in_keys=keys.data_ptr(), d_counts=cursor.data_ptr(),
-                       d_out_keys=out.data_ptr())
+                       d_out_keys=out.data_ptr(),
+                       d_parent_keys=None if parents is None else parents.data_ptr(),
+                       d_out_parents=None if parents is None else out_par.data_ptr())
         self._call(self.lib.ts_bfs_partition_scatter, a, "ts_bfs_partition_scatter")
-        return out, sizes
+        return out, sizes, out_par
 
     def new_table(self, capacity: int) -> torch.Tensor:
         return torch.full((capacity,), NONE, dtype=torch.int64, device=self.device)
@@ -143,7 +148,8 @@ class CudaBfsKernels:
         kw = {}
         if stats is not None:
             kw = dict(d_states_per_puzzle=stats.states.data_ptr(), d_solve_depth=stats.solve_depth.data_ptr(),
-                      d_goal_keys=None if stats.goal_keys is None else stats.goal_keys.data_ptr())
+                      d_goal_keys=None if stats.goal_keys is None else stats.goal_keys[0].data_ptr(),
+                      d_goal_parents=None if stats.goal_keys is None else stats.goal_keys[1].data_ptr())
         a = self._args(table_capacity=table.numel(), d_table=table.data_ptr(),
                        d_table_parent=None if parent_table is None else parent_table.data_ptr(), **kw)
         with torch.cuda.device(self.device):
@@ -211,18 +217,21 @@ class CudaBfsKernels:
         return self._xbuf[o: o + n]
 
     def insert(self, table: torch.Tensor, keys: torch.Tensor, parents: torch.Tensor | None = None,
-               parent_table: torch.Tensor | None = None, stats: "BfsStats | None" = None) -> tuple[torch.Tensor, int]:
+               parent_table: torch.Tensor | None = None, stats: "BfsStats | None" = None,
+               parent_per_item: bool = False) -> tuple[torch.Tensor, int]:
         """Insert keys; returns (keys that were new, with their goal bit; #goal successors seen).
         With `parent_table` (same capacity as `table`) every new key also records its parent:
-        `parents` must be the frontier `keys` was expanded from (None for roots).  The new keys
-        live in one of two alternating workspace buffers: valid until the insert after next."""
+        `parents` must be the frontier `keys` was expanded from (None for roots), or, with
+        `parent_per_item`, one parent per key (what `partition` wrote and the exchange delivered).
+        The new keys live in one of two alternating workspace buffers: valid until the insert after next."""
         out = self.workspace(f"out{self._flip}", keys.numel())
         self._flip ^= 1
         counts = torch.zeros(4, dtype=torch.int64, device=self.device)
         kw = {}
         if stats is not None:       # per-puzzle tallies kept by the kernel itself
             kw = dict(d_states_per_puzzle=stats.states.data_ptr(), d_solve_depth=stats.solve_depth.data_ptr(),
-                      d_goal_keys=None if stats.goal_keys is None else stats.goal_keys.data_ptr(), depth=stats.depth)
+                      d_goal_keys=None if stats.goal_keys is None else stats.goal_keys[0].data_ptr(),
+                      d_goal_parents=None if stats.goal_keys is None else stats.goal_keys[1].data_ptr(), depth=stats.depth)
         else:                       # hand the goal successors back to the caller instead
             if self._won_buf is None:
                 self._won_buf = torch.empty(self.WON_CAPACITY, dtype=torch.int64, device=self.device)
@@ -231,7 +240,8 @@ class CudaBfsKernels:
                        d_in_keys=keys.data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
                        d_counts=counts.data_ptr(),
                        d_parent_keys=None if parents is None else parents.data_ptr(),
-                       d_table_parent=None if parent_table is None else parent_table.data_ptr(), **kw)
+                       d_table_parent=None if parent_table is None else parent_table.data_ptr(),
+                       parent_per_item=int(parent_per_item), **kw)
         self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
         n_new, n_won, overflow, _ = counts.tolist()              # the one host sync of a BFS level
         if overflow:
@@ -244,16 +254,32 @@ class CudaBfsKernels:
 
 
     def traceback(self, table: torch.Tensor, parent_table: torch.Tensor, goals: torch.Tensor, max_moves: int):
-        """Shortest move strings of the goal states (NONE = no goal): (moves uint8[n, max_moves],
-        lengths int32[n])."""
-        n = goals.numel()
+        """Shortest move strings: goals = int64[2, n], the goal successor of every puzzle (NONE = no
+        goal) and the state it was generated from.  Returns (moves uint8[n, max_moves], lengths int32[n])."""
+        n = goals.shape[1]
         moves = torch.zeros(n, max_moves, dtype=torch.uint8, device=self.device)
         lengths = torch.full((n,), -1, dtype=torch.int32, device=self.device)
-        a = self._args(n_items=n, table_capacity=table.numel(), d_in_keys=goals.data_ptr(), d_table=table.data_ptr(),
-                       d_table_parent=parent_table.data_ptr(), d_moves=moves.data_ptr(), d_lengths=lengths.data_ptr(),
-                       max_moves=max_moves)
+        a = self._args(n_items=n, table_capacity=table.numel(), d_in_keys=goals[0].data_ptr(), d_parent_keys=goals[1].data_ptr(),
+                       d_table=table.data_ptr(), d_table_parent=parent_table.data_ptr(), d_moves=moves.data_ptr(),
+                       d_lengths=lengths.data_ptr(), max_moves=max_moves)
         self._call(self.lib.ts_bfs_traceback, a, "ts_bfs_traceback")
         return moves, lengths
+
+    def trace_step(self, table: torch.Tensor, parent_table: torch.Tensor, keys: torch.Tensor, rank: int, n_ranks: int,
+                   given_parents: torch.Tensor | None = None) -> torch.Tensor:
+        """One traceback step for the keys this rank owns: int64[2, n] = (parent, move) per key;
+        parent is INT64_MIN for NONE items and for keys of other ranks, -1 for a root, -2 for a broken
+        chain -- a MAX all-reduce over the ranks assembles the step for every key.  given_parents
+        (the last link of a solution): nothing is looked up, every rank answers for every key."""
+        n = keys.numel()
+        out = torch.zeros(2, n, dtype=torch.int64, device=self.device)
+        mv = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        a = self._args(n_items=n, n_ranks=n_ranks, rank=rank, table_capacity=table.numel(), d_in_keys=keys.data_ptr(),
+                       d_out_keys=out[0].data_ptr(), d_table=table.data_ptr(), d_table_parent=parent_table.data_ptr(),
+                       d_moves=mv.data_ptr(), d_parent_keys=None if given_parents is None else given_parents.data_ptr())
+        self._call(self.lib.ts_bfs_trace_step, a, "ts_bfs_trace_step")
+        out[1] = mv
+        return out
 
 
 class BfsSolver:
@@ -303,14 +329,15 @@ class BfsSolver:
         return r
 
     # ---- one exchange: every key travels to the rank that owns it -------------------------
-    def _exchange(self, keys: torch.Tensor) -> tuple[torch.Tensor, bool]:
-        """Returns (keys this rank owns, anything_sent_anywhere).  Two collectives: an
-        all_gather of the per-owner bucket sizes of every rank -- it doubles as the termination
-        test, a search is over when no rank has anything to send -- and the all-to-all of the
-        keys themselves."""
+    def _exchange(self, keys: torch.Tensor, parents: torch.Tensor | None = None):
+        """Returns (keys this rank owns, anything_sent_anywhere, their parents or None).  Two
+        collectives: an all_gather of the per-owner bucket sizes of every rank -- it doubles as the
+        termination test, a search is over when no rank has anything to send -- and the all-to-all
+        of the keys themselves (a second one for the parents, when a search records them: `parents`
+        is the frontier `keys` was expanded from)."""
         if self.world == 1:
-            return keys, bool(keys.numel())
-        send, sizes = self._timed("partition", self.k.partition, keys, self.world)
+            return keys, bool(keys.numel()), None
+        send, sizes, send_par = self._timed("partition", self.k.partition, keys, self.world, parents)
 
         def gather_sizes():
             mine = torch.tensor(sizes, dtype=torch.int64, device=send.device)
@@ -320,11 +347,14 @@ class BfsSolver:
         m = self._timed("all_gather_sizes", gather_sizes)
         rs = [m[src][self.rank] for src in range(self.world)]
         if not any(any(row) for row in m):
-            return send[:0], False
+            return send[:0], False, None
         ws = getattr(self.k, "workspace", None)
-        recv = ws("recv", sum(rs)) if ws else torch.empty(sum(rs), dtype=torch.int64, device=send.device)
-        self._timed("all_to_all", lambda: dist.all_to_all_single(recv, send, rs, sizes, group=self.group))
-        return recv, True
+
+        def deliver(name, what):
+            recv = ws(name, sum(rs)) if ws else torch.empty(sum(rs), dtype=torch.int64, device=send.device)
+            self._timed("all_to_all", lambda: dist.all_to_all_single(recv, what, rs, sizes, group=self.group))
+            return recv
+        return deliver("recv", send), True, None if send_par is None else deliver("recv_par", send_par)
 
     def _peer_level(self, parents: torch.Tensor, parity: int) -> tuple[torch.Tensor, bool]:
         """One level of the peer-memory exchange: K4x, then one all-reduce of the sent counts --
@@ -359,7 +389,7 @@ class BfsSolver:
         lvl = torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)       # per level: new keys, goal successors, overflow, -
         xlvl = torch.zeros(n_lvl, 4, dtype=torch.int64, device=dev)      # per level: -, -, inbox overflow, keys sent (all-reduced)
         # depth 0: seeds to their owners through the NCCL path, ordinary insert
-        mine, _ = self._exchange(k.seed())
+        mine, _, _ = self._exchange(k.seed())
         seeds, _ = k.insert(table, mine, None, None, stats) if stats is not None else k.insert(table, mine)
         front[0][: seeds.numel()].copy_(seeds)
         lvl[0, 0] = seeds.numel()
@@ -412,7 +442,7 @@ class BfsSolver:
         k, P, dev = self.k, self.n_puzzles, self.k.device
         table = k.new_table(self.table_capacity)
         parent_table = k.new_table(self.table_capacity) if with_paths else None
-        goal_keys = torch.full((P,), NONE, dtype=torch.int64, device=dev) if with_paths else None
+        goal_keys = torch.full((2, P), NONE, dtype=torch.int64, device=dev) if with_paths else None
         states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
         depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
         stats = BfsStats(states_pp, depth_pp, goal_keys) if per_puzzle else None
@@ -463,14 +493,56 @@ class BfsSolver:
         return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
                          solve_depth_per_puzzle=depth_pp, generated=generated, solutions=solutions)
 
+    def _trace_over_ranks(self, table, parent_table, goal_keys: torch.Tensor, max_moves: int):
+        """Shortest move strings when the visited set (and its parent links) is spread over the
+        ranks.  A puzzle has ONE goal state (the targets, canonical), so exactly one rank holds its
+        goal key; after a MAX all-reduce every rank knows all of them.  Then one collective per
+        move: each rank looks up the keys it owns (ts_bfs_trace_step), the MAX all-reduce of the
+        (parent, move) pairs gives every rank the whole step.  Returns what `traceback` returns."""
+        k, dev, P = self.k, goal_keys.device, goal_keys.shape[1]
+        goals = torch.where(goal_keys == NONE, goal_keys, goal_keys & 0x7FFFFFFFFFFFFFFF)     # [2, P]: goal successor, its parent
+        dist.all_reduce(goals, op=dist.ReduceOp.MAX, group=self.group)
+        cur, last_from = goals[0].contiguous(), goals[1].contiguous()
+        has_goal = cur != NONE
+        moves = torch.zeros(P, max_moves, dtype=torch.uint8, device=dev)
+        lengths = torch.zeros(P, dtype=torch.int64, device=dev)
+        broken = torch.zeros(P, dtype=torch.bool, device=dev)
+        for step in range(max_moves + 1):
+            if step == 0:     # the last link is the recorded one (a puzzle that starts on its goal: the root has no parent)
+                pm = k.trace_step(table, parent_table, cur, self.rank, self.world, given_parents=last_from)
+            else:
+                pm = k.trace_step(table, parent_table, cur, self.rank, self.world)
+                dist.all_reduce(pm, op=dist.ReduceOp.MAX, group=self.group)
+            parent, move = pm[0], pm[1]
+            active = parent >= 0
+            broken |= (parent < -1) & (cur != NONE)          # -2: broken chain; INT64_MIN: no rank knew the key
+            if step == 0:
+                broken |= (parent == -1) & (cur != NONE)     # a goal successor always has a parent
+            if step == max_moves:
+                broken |= active                             # longer than the depth the search reported
+                break
+            if not bool(active.any()):
+                break
+            moves[:, step] = torch.where(active, move, torch.zeros_like(move)).to(torch.uint8)
+            lengths += active
+            cur = torch.where(active, parent, torch.full_like(parent, NONE))
+        # the chain was walked goal -> root: reverse each string over its own length
+        idx = (lengths[:, None] - 1 - torch.arange(max_moves, device=dev)[None, :]).clamp_(min=0)
+        moves = moves.gather(1, idx)
+        lengths = torch.where(has_goal & ~broken, lengths, torch.full_like(lengths, -1)).to(torch.int32)
+        return moves, lengths
+
     def solve(self, max_depth: int = 1 << 20, per_puzzle: bool = True, with_paths: bool = False,
               device_driven: bool | None = None) -> BfsResult:
-        """Search every puzzle to exhaustion (or max_depth).  with_paths (single rank only): also
-        record parents and return a shortest solution string per puzzle.
+        """Search every puzzle to exhaustion (or max_depth).  with_paths: also record parents and
+        return a shortest solution string per puzzle; over several ranks the
+        parents travel with the keys (host-driven levels, all-to-all exchange) and the chains are
+        walked one step per collective, every rank answering for the keys it owns.
         device_driven (default: on for a single rank on the CUDA kernels): see _solve_on_device."""
         k, P = self.k, self.n_puzzles
-        if with_paths and (self.world > 1 or not per_puzzle):
-            raise ValueError("with_paths needs a single-rank search with per_puzzle statistics")
+        if with_paths and not per_puzzle:
+            raise ValueError("with_paths needs per_puzzle statistics")
+        dist_paths = with_paths and self.world > 1
         can = self.world == 1 and isinstance(k, CudaBfsKernels) and not self.profile
         can_p2p = self.world > 1 and self.exchange == "p2p" and not self.profile and not with_paths
         if device_driven is None:
@@ -487,7 +559,7 @@ class BfsSolver:
         dev = k.device
         if hasattr(k, "reserve"):
             k.reserve(max(1 << 16, min(self.table_capacity // 8, 1 << 27)))
-        goal_keys = torch.full((P,), NONE, dtype=torch.int64, device=dev) if with_paths else None
+        goal_keys = torch.full((2, P), NONE, dtype=torch.int64, device=dev) if with_paths else None
         states_pp = torch.zeros(P, dtype=torch.int64, device=dev) if per_puzzle else None
         depth_pp = torch.full((P,), 1 << 30, dtype=torch.int32, device=dev) if per_puzzle else None
         single_puzzle_keys = getattr(k, "t", None) is not None and k.t.n_tiles > 4   # no id bits in the key
@@ -501,13 +573,13 @@ class BfsSolver:
         stats = BfsStats(states_pp, depth_pp, goal_keys) if per_puzzle and isinstance(k, CudaBfsKernels) else None
 
         def insert(keys, parents, depth):
-            extra = (parents, parent_table) if with_paths else ()
             if stats is not None:
                 stats.depth = depth
-                return k.insert(table, keys, *(extra or (None, None)), stats)
-            return k.insert(table, keys, *extra)
+            if with_paths:                                    # several ranks: one parent per key, as delivered
+                return k.insert(table, keys, parents, parent_table, stats, parent_per_item=dist_paths and parents is not None)
+            return k.insert(table, keys, None, None, stats) if stats is not None else k.insert(table, keys)
 
-        mine, _ = self._exchange(k.seed())
+        mine, _, _ = self._exchange(k.seed())
         frontier, _ = insert(mine, None, 0)
         # per-rank tallies; summed over the ranks once, after the search
         local_levels, local_won, generated = [frontier.numel()], [0], 0
@@ -520,25 +592,32 @@ class BfsSolver:
         depth = 0
         while depth < max_depth:
             parents = frontier                                # expand / insert ignore the goal bit of their inputs
-            if self.exchange == "p2p":
+            recv_parents = parents
+            if self.exchange == "p2p" and not dist_paths:
                 recv, alive = self._timed("expand_exchange", self._peer_level, parents, depth & 1)
             else:
                 succ = self._timed("expand", k.expand, parents)
                 # single rank: successors go straight to the table (it skips NONE) and successor i stays
-                # next to its parent i // 4; several ranks: bucket by owner and exchange
-                recv, alive = self._exchange(succ)
+                # next to its parent i // 4; several ranks: bucket by owner and exchange (the fused
+                # peer-memory kernel moves keys only, so a search that records parents takes this path)
+                recv, alive, got = self._exchange(succ, parents if dist_paths else None)
+                recv_parents = got if dist_paths else parents
             if not alive:
                 break
             depth += 1
             generated += 4 * parents.numel()
-            frontier, n_won = self._timed("insert", insert, recv, parents, depth)
+            frontier, n_won = self._timed("insert", insert, recv, recv_parents, depth)
             if per_puzzle and n_won and stats is None:
                 won = getattr(k, "last_won", None)
                 if won is None:                              # stand-in kernels / overflowed buffer: scan
                     won = recv[(recv < 0) & (recv != NONE)]
-                if with_paths:                               # first goal state seen for a puzzle = a shortest solution
-                    fresh = won[depth_pp[pid_of(won)] >= (1 << 30)]
-                    goal_keys[pid_of(fresh)] = fresh
+                if with_paths:                               # first goal successor seen for a puzzle = a shortest solution
+                    at = torch.nonzero((recv < 0) & (recv != NONE)).flatten()
+                    won = recv[at]
+                    won_from = recv_parents[at if dist_paths else at // 4]
+                    fresh = depth_pp[pid_of(won)] >= (1 << 30)
+                    goal_keys[0, pid_of(won[fresh])] = won[fresh]
+                    goal_keys[1, pid_of(won[fresh])] = won_from[fresh] & 0x7FFFFFFFFFFFFFFF
                 d = torch.full((won.numel(),), depth, dtype=torch.int32, device=dev)
                 depth_pp.scatter_reduce_(0, pid_of(won), d, reduce="amin")
             local_levels.append(frontier.numel())
@@ -563,7 +642,10 @@ class BfsSolver:
         solutions = None
         if with_paths:
             max_moves = max(1, int(depth_pp.max()))
-            moves, lengths = k.traceback(table, parent_table, goal_keys, max_moves)
+            if dist_paths:
+                moves, lengths = self._trace_over_ranks(table, parent_table, goal_keys, max_moves)
+            else:
+                moves, lengths = k.traceback(table, parent_table, goal_keys, max_moves)
             mv, ln = moves.cpu().tolist(), lengths.cpu().tolist()
             solutions = ["".join("UDLR"[m] for m in mv[i][:ln[i]]) if ln[i] >= 0 else None for i in range(P)]
         return BfsResult(n_states=sum(levels), levels=levels, solve_depth=solve_depth, states_per_puzzle=states_pp,
@@ -705,7 +787,7 @@ class LocalBfs:
         cap = self.fallback_table_capacity
         while True:
             try:
-                return BfsSolver(sub, table_capacity=cap, group=self.group).solve(max_depth=max_depth, with_paths=with_paths and self.world == 1)
+                return BfsSolver(sub, table_capacity=cap, group=self.group).solve(max_depth=max_depth, with_paths=with_paths)
             except RuntimeError as e:                     # visited table full: double it
                 if "table" not in str(e) or cap >= 1 << 32:
                     raise

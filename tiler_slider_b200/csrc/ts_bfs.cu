@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(256) bfs_partition_scatter_kernel(const ts_bfs
     if (threadIdx.x < a.n_ranks && hist[threadIdx.x])
         base[threadIdx.x] = atomicAdd((unsigned long long*)&a.d_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
     __syncthreads();
-    if (live) a.d_out_keys[base[owner] + slot] = key;
+    if (live) {
+        a.d_out_keys[base[owner] + slot] = key;
+        // with parents: the key it was expanded from travels to the owner beside it
+        if (a.d_out_parents) a.d_out_parents[base[owner] + slot] = a.d_parent_keys[i >> 2] & ~BFS_WON_BIT;
+    }
 }
 
 // K4x: expand + bucket + exchange over NVLink peer memory in one kernel.  A block keeps its 1024
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
                 old = atomicCAS((unsigned long long*)&a.d_table[slot], (unsigned long long)BFS_NONE, (unsigned long long)key);
             else if (old != key) { slot = (slot + 1) & mask; continue; }
             if (old == BFS_NONE) {
-                if (a.d_table_parent) a.d_table_parent[slot] = a.d_parent_keys ? (a.d_parent_keys[i >> 2] & ~BFS_WON_BIT) : BFS_NONE;
+                if (a.d_table_parent) a.d_table_parent[slot] = a.d_parent_keys ? (a.d_parent_keys[a.parent_per_item ? i : (i >> 2)] & ~BFS_WON_BIT) : BFS_NONE;
                 is_new = true;
                 break;
             }
@@ -314,7 +318,11 @@ __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args 
     }
     if (a.d_solve_depth && won) {
         const int before = atomicMin(&a.d_solve_depth[pid], a.depth);
-        if (before > a.depth && a.d_goal_keys) a.d_goal_keys[pid] = raw;
+        if (before > a.depth && a.d_goal_keys) {
+            a.d_goal_keys[pid] = raw;
+            if (a.d_goal_parents && a.d_parent_keys)
+                a.d_goal_parents[pid] = a.d_parent_keys[a.parent_per_item ? i : (i >> 2)] & ~BFS_WON_BIT;
+        }
     }
     if (won_mask) {
         const int leader = __ffs(won_mask) - 1;
@@ -343,11 +351,31 @@ __device__ __forceinline__ int64_t table_find(const uint64_t* table, int64_t cap
     return -1;
 }
 
+// the move that leads from `parent` to `key` (both without the goal bit): the smallest move
+// index whose slide of the parent reproduces the child; -1 if none does
+template <int S, int T>
+__device__ __forceinline__ int move_between(const ts_bfs_args& a, uint64_t parent, uint64_t key) {
+    constexpr int PR = (T + 3) / 4, NB = board_bytes(S);
+    uint32_t q0[PR];
+    uint64_t pid;
+    split_key<T>(parent, q0, pid);
+    const uint64_t walls = load_board_elem<NB>(a.d_walls, (size_t)a.puzzle_capacity, (size_t)pid);
+    int move = -1;
+    for (uint32_t d = 0; d < 4 && move < 0; ++d) {
+        uint32_t q[PR];
+#pragma unroll
+        for (int w = 0; w < PR; ++w) q[w] = q0[w];
+        slide_env<S, T>(q, walls, d >> 1, (d & 1u) ^ 1u);
+        if (a.goal_mode == TS_GOAL_SET) sort_bytes<T>(q);
+        if (make_key<T>(q, pid) == key) move = (int)d;
+    }
+    return move;
+}
+
 // shortest move string of each goal state: walk the parent chain, recover every move by
-// re-sliding the parent (smallest move index that reproduces the child), reverse at the end
+// re-sliding the parent, reverse at the end
 template <int S, int T>
 __global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a) {
-    constexpr int PR = (T + 3) / 4, NB = board_bytes(S);
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= a.n_items) return;
     uint8_t* out = a.d_moves + (size_t)i * a.max_moves;
@@ -356,25 +384,21 @@ __global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a)
     key &= ~BFS_WON_BIT;
     int len = 0;
     bool ok = true;
+    {   // the last link is given, not looked up: the goal state's table entry is that of its FIRST
+        // visit, which for a puzzle that starts on its goal is the root (no parent)
+        const uint64_t from = a.d_parent_keys[i];
+        const int move = from == BFS_NONE ? -1 : move_between<S, T>(a, from & ~BFS_WON_BIT, key);
+        if (move < 0) { a.d_lengths[i] = -1; return; }
+        out[len++] = (uint8_t)move;
+        key = from & ~BFS_WON_BIT;
+    }
     while (ok) {
         const int64_t slot = table_find(a.d_table, a.table_capacity, key);
         if (slot < 0) { ok = false; break; }
         const uint64_t parent = a.d_table_parent[slot];
         if (parent == BFS_NONE) break;                     // reached a root
         if (len >= a.max_moves) { ok = false; break; }
-        uint32_t q0[PR];
-        uint64_t pid;
-        split_key<T>(parent, q0, pid);
-        const uint64_t walls = load_board_elem<NB>(a.d_walls, (size_t)a.puzzle_capacity, (size_t)pid);
-        int move = -1;
-        for (uint32_t d = 0; d < 4 && move < 0; ++d) {
-            uint32_t q[PR];
-#pragma unroll
-            for (int w = 0; w < PR; ++w) q[w] = q0[w];
-            slide_env<S, T>(q, walls, d >> 1, (d & 1u) ^ 1u);
-            if (a.goal_mode == TS_GOAL_SET) sort_bytes<T>(q);
-            if (make_key<T>(q, pid) == key) move = (int)d;
-        }
+        const int move = move_between<S, T>(a, parent, key);
         if (move < 0) { ok = false; break; }
         out[len++] = (uint8_t)move;
         key = parent;
@@ -382,6 +406,36 @@ __global__ void __launch_bounds__(128) bfs_traceback_kernel(const ts_bfs_args a)
     if (!ok) { a.d_lengths[i] = -1; return; }
     for (int l = 0, r = len - 1; l < r; ++l, --r) { const uint8_t t = out[l]; out[l] = out[r]; out[r] = t; }
     a.d_lengths[i] = len;
+}
+
+// one traceback step over a visited set that is spread over several owners: this rank answers
+// for the keys it owns, every other item gets the smallest int64 so that a MAX all-reduce over
+// the owners assembles the step (see ts_bfs_trace_step in the header)
+constexpr uint64_t TRACE_NOT_MINE = 0x8000000000000000ull, TRACE_BROKEN = 0xFFFFFFFFFFFFFFFEull;
+template <int S, int T>
+__global__ void __launch_bounds__(128) bfs_trace_step_kernel(const ts_bfs_args a) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= a.n_items) return;
+    uint64_t key = a.d_in_keys[i], out = TRACE_NOT_MINE;
+    int move = 0;
+    if (key != BFS_NONE) {
+        key &= ~BFS_WON_BIT;
+        if (a.d_parent_keys) {                       // the last link of a solution: given, on every rank
+            out = a.d_parent_keys[i];
+            move = out == BFS_NONE ? -1 : move_between<S, T>(a, out & ~BFS_WON_BIT, key);
+            out = move < 0 ? TRACE_BROKEN : (out & ~BFS_WON_BIT);
+            move = move < 0 ? 0 : move;
+        } else if (a.n_ranks <= 1 || key_owner(key, (uint32_t)a.n_ranks) == (uint32_t)a.rank) {
+            const int64_t slot = table_find(a.d_table, a.table_capacity, key);
+            out = slot < 0 ? TRACE_BROKEN : a.d_table_parent[slot];
+            if (slot >= 0 && out != BFS_NONE) {
+                move = move_between<S, T>(a, out, key);
+                if (move < 0) { out = TRACE_BROKEN; move = 0; }
+            }
+        }
+    }
+    a.d_out_keys[i] = out;
+    a.d_moves[i] = (uint8_t)move;
 }
 
 template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a, cudaStream_t st) {
@@ -393,6 +447,7 @@ template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a,
         if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
         else if (op == 1) bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);           \
         else if (op == 3) bfs_expand_exchange_kernel<S, T><<<blocks, 256, 0, st>>>(a);  \
+        else if (op == 4) bfs_trace_step_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
         else bfs_traceback_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
         break;
     switch (a.n_tiles) {
@@ -495,9 +550,18 @@ int ts_bfs_levels(const ts_bfs_args* a, int32_t first_depth, int32_t n_levels, u
 int ts_bfs_traceback(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, true)) return rc;
     if (a->n_items == 0) return 0;
-    if (!a->d_walls || !a->d_in_keys || !a->d_table || !a->d_table_parent || !a->d_moves || !a->d_lengths) return TS_E_NULL_POINTER;
+    if (!a->d_walls || !a->d_in_keys || !a->d_parent_keys || !a->d_table || !a->d_table_parent || !a->d_moves || !a->d_lengths) return TS_E_NULL_POINTER;
     if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1)) || a->max_moves < 1) return TS_E_BAD_ARGUMENT;
     return (int)bfs_dispatch(2, *a, (cudaStream_t)stream);
+}
+
+int ts_bfs_trace_step(const ts_bfs_args* a, void* stream) {
+    if (int rc = bfs_check(a, true)) return rc;
+    if (a->n_items == 0) return 0;
+    if (!a->d_walls || !a->d_in_keys || !a->d_out_keys || !a->d_table || !a->d_table_parent || !a->d_moves) return TS_E_NULL_POINTER;
+    if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
+    if (a->n_ranks < 1 || a->n_ranks > 64 || a->rank < 0 || a->rank >= a->n_ranks) return TS_E_BAD_ARGUMENT;
+    return (int)bfs_dispatch(4, *a, (cudaStream_t)stream);
 }
 
 int ts_bfs_partition_count(const ts_bfs_args* a, void* stream) {
@@ -514,6 +578,7 @@ int ts_bfs_partition_scatter(const ts_bfs_args* a, void* stream) {
     if (a->n_ranks < 1 || a->n_ranks > 64) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
     if (!a->d_in_keys || !a->d_counts) return TS_E_NULL_POINTER;   // d_out_keys may be NULL when every key is NONE
+    if (a->d_out_parents && !a->d_parent_keys) return TS_E_NULL_POINTER;
     bfs_partition_scatter_kernel<<<(unsigned)((a->n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
