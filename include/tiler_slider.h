@@ -280,23 +280,14 @@ typedef struct ts_bfs_args {
     int64_t *d_states_per_puzzle;
     int32_t *d_solve_depth;
     uint64_t *d_goal_keys;
-    int32_t depth;
-    int32_t xchg_staged;                /* ts_bfs_expand_exchange: 1 = bucket the round in shared memory, write whole runs */
+    int32_t depth, reserved2;
     /* ts_bfs_expand_exchange (multi-GPU, peer memory): d_peer_bufs[r] = rank r's exchange buffer
      * as mapped into THIS process (NVLink peer mapping, e.g. torch symmetric memory):
      *   word 0, 1          arrival cursors of inbox 0 / inbox 1 (keys received so far)
      *   word 2             set to 1 when an inbox overflowed
      *   word TS_BFS_XHDR + p * inbox_capacity ...   inbox p (u64 keys)
-     *   words 64 + p * 64 + s          (sender-partitioned) keys sender s left in its segment of inbox p
      * The successors of d_in_keys are written straight into inbox `parity` of their owner rank
-     * (hash(key) % n_ranks); d_counts[3] += number of keys sent.
-     * Sender-partitioned inboxes (seg_capacity > 0, needs xchg_staged and rank): inbox p is cut into
-     * n_ranks segments of seg_capacity keys, segment s written by rank s only; room is reserved
-     * with local atomics on d_send_state (192 zeroed words of the caller's own memory) and the last
-     * block of the launch publishes this rank's counts into the owners' headers -- no remote
-     * atomics.  Every rank must launch every level, with n_items = 0 if it has nothing to expand.
-     * ts_bfs_hash_insert then reads such an inbox with d_in_keys = the inbox, d_seg_counts = its
-     * header words 64 + p * 64, the same seg_capacity and n_ranks. */
+     * (hash(key) % n_ranks); d_counts[3] += number of keys sent. */
     uint64_t *const *d_peer_bufs;
     int64_t inbox_capacity;
     int32_t parity, parent_per_item;
@@ -318,11 +309,8 @@ typedef struct ts_bfs_args {
      * the goal is won by its first step (a root is never a goal successor), and the root has no
      * parent. */
     uint64_t *d_goal_parents;
-    int64_t seg_capacity;
-    uint64_t *d_send_state;
-    const uint64_t *d_seg_counts;
 } ts_bfs_args;
-#define TS_BFS_XHDR 512
+#define TS_BFS_XHDR 16
 int ts_bfs_seed(const ts_bfs_args *a, void *stream);
 int ts_bfs_expand(const ts_bfs_args *a, void *stream);
 int ts_bfs_partition_count(const ts_bfs_args *a, void *stream);

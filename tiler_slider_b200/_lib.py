@@ -76,10 +76,9 @@ class BfsArgs(C.Structure):
                 ("d_parent_keys", _vp), ("d_table_parent", _vp), ("d_moves", _vp), ("d_lengths", _vp),
                 ("max_moves", _i64), ("d_won_keys", _vp), ("won_capacity", _i64),
                 ("d_states_per_puzzle", _vp), ("d_solve_depth", _vp), ("d_goal_keys", _vp),
-                ("depth", _i32), ("xchg_staged", _i32),
+                ("depth", _i32), ("reserved2", _i32),
                 ("d_peer_bufs", _vp), ("inbox_capacity", _i64), ("parity", _i32), ("parent_per_item", _i32),
-                ("d_n_items", _vp), ("n_items_scale", _i64), ("d_out_parents", _vp), ("d_goal_parents", _vp),
-                ("seg_capacity", _i64), ("d_send_state", _vp), ("d_seg_counts", _vp)]
+                ("d_n_items", _vp), ("n_items_scale", _i64), ("d_out_parents", _vp), ("d_goal_parents", _vp)]
 
 
 class BfsLocalArgs(C.Structure):

@@ -23,7 +23,6 @@ tensors over gloo with a CPU stand-in for the kernels (tests/test_bfs_gloo.py).
 from __future__ import annotations
 
 import ctypes as C
-import os
 import time
 from dataclasses import dataclass, field
 from typing import Sequence
@@ -159,15 +158,7 @@ class CudaBfsKernels:
                                          torch.cuda.current_stream(self.device).cuda_stream), "ts_bfs_levels")
 
     # ---- exchange through NVLink peer memory (ts_bfs_expand_exchange) ----------------------
-    XHDR = 512                                  # TS_BFS_XHDR: header words ahead of the two inboxes
-    SEG_COUNTS = 64                             # header words [64 + parity * 64 + sender]: published segment counts
-    SEND_STATE = 192                            # header words [192 ...): this rank's send cursors (local use only)
-    # how ts_bfs_expand_exchange delivers: "cursor" = a remote atomic per owner and round on the owner's
-    # arrival cursor, keys stored from registers; "staged" = same cursors, the round bucketed in shared
-    # memory and written as whole runs; "segments" = staged + sender-partitioned inboxes (local atomics,
-    # counts published once per level)
-    XCHG_MODES = ("cursor", "staged", "segments")
-    XCHG_DEFAULT = "cursor"
+    XHDR = 16                                   # TS_BFS_XHDR: header words ahead of the two inboxes
 
     def setup_peer_exchange(self, group, inbox_capacity: int) -> bool:
         """Allocate this rank's exchange buffer (two inboxes + cursors) in symmetric memory and
@@ -183,12 +174,7 @@ class CudaBfsKernels:
             self.peer_exchange_error = repr(e)
             return False
         buf[: self.XHDR].zero_()
-        self.xchg_mode = os.environ.get("TS_BFS_XCHG", self.XCHG_DEFAULT)
-        if self.xchg_mode not in self.XCHG_MODES:
-            raise ValueError(f"TS_BFS_XCHG must be one of {self.XCHG_MODES}")
         self._xbuf, self._xhdl, self._xcap = buf, hdl, int(inbox_capacity)
-        self._xrank = dist.get_rank(group)
-        self._xseg = int(inbox_capacity) // len(hdl.buffer_ptrs) if self.xchg_mode == "segments" else 0
         self._xpeers = torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=self.device)
         self._xworld = len(hdl.buffer_ptrs)
         self._xcounts = torch.zeros(4, dtype=torch.int64, device=self.device)
@@ -196,31 +182,20 @@ class CudaBfsKernels:
         hdl.barrier()                           # every header is zero before anyone sends
         return True
 
-    def _xchg_args(self) -> dict:
-        return dict(n_ranks=self._xworld, rank=self._xrank, d_peer_bufs=self._xpeers.data_ptr(), inbox_capacity=self._xcap,
-                    xchg_staged=int(self.xchg_mode != "cursor"), seg_capacity=self._xseg,
-                    d_send_state=self._xbuf[self.SEND_STATE:].data_ptr())
-
-    def _inbox_args(self, parity: int) -> dict:
-        """how ts_bfs_hash_insert finds the keys that arrived in inbox `parity`"""
-        o = self.XHDR + parity * self._xcap
-        if self._xseg:
-            return dict(n_items=self._xseg * self._xworld, n_ranks=self._xworld, seg_capacity=self._xseg,
-                        d_in_keys=self._xbuf[o:].data_ptr(), d_seg_counts=self._xbuf[self.SEG_COUNTS + parity * 64:].data_ptr())
-        return dict(n_items=self._xcap, d_in_keys=self._xbuf[o:].data_ptr(), d_n_items=self._xbuf[parity:].data_ptr(), n_items_scale=1)
-
     def expand_exchange(self, frontier: torch.Tensor, parity: int) -> None:
         """K4x: successors of `frontier` go straight into inbox `parity` of their owner ranks;
         self._xcounts[3] accumulates the number of keys this rank sent."""
-        a = self._args(n_items=frontier.numel(), d_in_keys=frontier.data_ptr() if frontier.numel() else None,
-                       d_counts=self._xcounts.data_ptr(), parity=parity, **self._xchg_args())
+        a = self._args(n_items=frontier.numel(), n_ranks=self._xworld, d_in_keys=frontier.data_ptr(),
+                       d_counts=self._xcounts.data_ptr(), d_peer_bufs=self._xpeers.data_ptr(),
+                       inbox_capacity=self._xcap, parity=parity)
         self._call(self.lib.ts_bfs_expand_exchange, a, "ts_bfs_expand_exchange")
 
     def expand_exchange_on_device(self, front: torch.Tensor, n_ptr: int, parity: int, xcounts: torch.Tensor) -> None:
         """K4x on a frontier whose size sits in device memory (*n_ptr); xcounts = int64[4] of this
         level: [2] overflow, [3] keys sent."""
-        a = self._args(n_items=front.numel(), d_in_keys=front.data_ptr(), d_counts=xcounts.data_ptr(), parity=parity,
-                       d_n_items=n_ptr, n_items_scale=1, **self._xchg_args())
+        a = self._args(n_items=front.numel(), n_ranks=self._xworld, d_in_keys=front.data_ptr(),
+                       d_counts=xcounts.data_ptr(), d_peer_bufs=self._xpeers.data_ptr(),
+                       inbox_capacity=self._xcap, parity=parity, d_n_items=n_ptr, n_items_scale=1)
         self._call(self.lib.ts_bfs_expand_exchange, a, "ts_bfs_expand_exchange")
 
     def insert_inbox_on_device(self, table: torch.Tensor, parity: int, out: torch.Tensor, counts: torch.Tensor,
@@ -231,18 +206,15 @@ class CudaBfsKernels:
         if stats is not None:
             kw = dict(d_states_per_puzzle=stats.states.data_ptr(), d_solve_depth=stats.solve_depth.data_ptr(),
                       d_goal_keys=None, depth=depth)
-        a = self._args(table_capacity=table.numel(), out_capacity=out.numel(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
-                       d_counts=counts.data_ptr(), **self._inbox_args(parity), **kw)
+        o = self.XHDR + parity * self._xcap
+        a = self._args(n_items=self._xcap, table_capacity=table.numel(), out_capacity=out.numel(),
+                       d_in_keys=self._xbuf[o:].data_ptr(), d_out_keys=out.data_ptr(), d_table=table.data_ptr(),
+                       d_counts=counts.data_ptr(), d_n_items=self._xbuf[parity:].data_ptr(), n_items_scale=1, **kw)
         self._call(self.lib.ts_bfs_hash_insert, a, "ts_bfs_hash_insert")
 
-    def inbox(self, parity: int) -> torch.Tensor:
-        """the keys that arrived in inbox `parity` (host-driven levels: reads the counts back)"""
+    def inbox(self, parity: int, n: int) -> torch.Tensor:
         o = self.XHDR + parity * self._xcap
-        if not self._xseg:
-            return self._xbuf[o: o + int(self._xbuf[parity].item())]
-        c0 = self.SEG_COUNTS + parity * 64
-        counts = self._xbuf[c0: c0 + self._xworld].tolist()
-        return torch.cat([self._xbuf[o + s * self._xseg: o + s * self._xseg + min(c, self._xseg)] for s, c in enumerate(counts)])
+        return self._xbuf[o: o + n]
 
     def insert(self, table: torch.Tensor, keys: torch.Tensor, parents: torch.Tensor | None = None,
                parent_table: torch.Tensor | None = None, stats: "BfsStats | None" = None,
@@ -393,12 +365,11 @@ class BfsSolver:
         k.expand_exchange(parents, parity)
         sent = k._xcounts[3:4].clone()
         dist.all_reduce(sent, group=self.group)
-        n_sent, overflow = torch.cat([sent, k._xbuf[2:3] + k._xcounts[2:3]]).tolist()
+        n_sent, n_in, overflow = torch.cat([sent, k._xbuf[parity: parity + 1], k._xbuf[2:3] + k._xcounts[2:3]]).tolist()
         if overflow:
             raise RuntimeError("BFS exchange inbox is full: raise table_capacity")
-        recv = k.inbox(parity)
         k._xbuf[parity: parity + 1].zero_()        # nobody writes this inbox again before the level after next
-        return recv, bool(n_sent)
+        return k.inbox(parity, n_in), bool(n_sent)
 
     def _solve_p2p_on_device(self, max_depth: int, per_puzzle: bool) -> BfsResult:
         """Several ranks, peer-memory exchange, frontier sizes on the device.  Per level and rank:

@@ -258,146 +258,16 @@ __global__ void __launch_bounds__(256) bfs_expand_exchange_kernel(const ts_bfs_a
     __threadfence_system();
 }
 
-// K4x, second form (ts_bfs_args.xchg_staged): the round's successors are first bucketed by owner in
-// shared memory, then written out in owner order, so that a warp's store covers 256 contiguous bytes
-// of one inbox (full NVLink packets) instead of ~4 keys for each of 8 owners.  With seg_capacity > 0
-// the inboxes are sender-partitioned as well: inbox p of rank r is cut into one segment per sender,
-// a block reserves room in this rank's segment of the owner's inbox with a LOCAL atomic
-// (d_send_state), and the last block to finish publishes this rank's segment counts to the owners
-// (one 8-byte remote store per owner and level) -- no remote atomics at all.
-constexpr int XHDR_SEG_COUNTS = 64;      // header words [64 + parity * 64 + sender]: keys sender wrote into its segment
-template <int S, int T>
-__global__ void __launch_bounds__(256) bfs_expand_exchange_staged_kernel(const ts_bfs_args a) {
-    constexpr int ROUND_KEYS = 256 * XCHG_STATES * 4;
-    __shared__ uint64_t stage[ROUND_KEYS];               // 32 KB
-    __shared__ unsigned int hist[64], start[65];
-    __shared__ unsigned long long base[64];
-    __shared__ bool is_last;
-    const int64_t n_items = item_count(a);
-    constexpr int64_t ROUND = 256 * XCHG_STATES;
-    const bool seg = a.seg_capacity > 0;
-    for (int64_t first = (int64_t)blockIdx.x * ROUND; first < n_items; first += (int64_t)gridDim.x * ROUND) {
-        if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-        __syncthreads();
-        uint64_t key[XCHG_STATES][4];
-        uint32_t where[XCHG_STATES][4];                    // owner | slot << 8
-#pragma unroll
-        for (int s = 0; s < XCHG_STATES; ++s) {
-            const int64_t i = first + s * 256 + threadIdx.x;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) key[s][d] = BFS_NONE;
-            if (i < n_items) successors<S, T>(a, a.d_in_keys[i], key[s]);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const bool live = key[s][d] != BFS_NONE;
-                const uint32_t owner = live ? key_owner(key[s][d], (uint32_t)a.n_ranks) : 0u;
-                where[s][d] = owner | (block_bucket_slot(hist, live, owner) << 8);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < a.n_ranks) {
-            const unsigned n = hist[threadIdx.x];
-            unsigned long long b = ~0ull;
-            if (n) {
-                uint64_t* peer = a.d_peer_bufs[threadIdx.x];
-                unsigned long long limit;
-                if (seg) {
-                    b = atomicAdd((unsigned long long*)&a.d_send_state[a.parity * 64 + threadIdx.x], (unsigned long long)n);
-                    limit = (unsigned long long)a.seg_capacity;
-                } else {
-                    b = atomicAdd_system((unsigned long long*)(peer + a.parity), (unsigned long long)n);
-                    limit = (unsigned long long)a.inbox_capacity;
-                }
-                if (b + n > limit) {                                     // inbox / segment full: drop and report
-                    peer[2] = 1;
-                    a.d_counts[2] = 1;
-                    b = ~0ull;
-                } else if (seg) {
-                    b += (unsigned long long)a.rank * (unsigned long long)a.seg_capacity;
-                }
-                atomicAdd((unsigned long long*)&a.d_counts[3], (unsigned long long)n);
-            }
-            base[threadIdx.x] = b;
-        }
-        if (threadIdx.x == 255) {                                        // where each owner's run starts in the stage
-            unsigned acc = 0;
-            for (int o = 0; o < a.n_ranks; ++o) { start[o] = acc; acc += hist[o]; }
-            start[a.n_ranks] = acc;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < XCHG_STATES; ++s)
-#pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if (key[s][d] != BFS_NONE) stage[start[where[s][d] & 0xFFu] + (where[s][d] >> 8)] = key[s][d];
-        __syncthreads();
-        const unsigned total = start[a.n_ranks];
-        for (unsigned j = threadIdx.x; j < total; j += 256) {
-            int o = 0;
-            while (j >= start[o + 1]) ++o;
-            const unsigned long long b = base[o];
-            if (b == ~0ull) continue;
-            uint64_t* inbox = a.d_peer_bufs[o] + TS_BFS_XHDR + (int64_t)a.parity * a.inbox_capacity;
-            inbox[b + (j - start[o])] = stage[j];
-        }
-        __syncthreads();                                                  // stage / hist / base are reused by the next round
-    }
-    __threadfence_system();
-    if (seg) {     // the last block to get here tells every owner how many keys this rank left in its segment
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const unsigned long long t = atomicAdd((unsigned long long*)&a.d_send_state[128 + a.parity], 1ull);
-            is_last = t == (unsigned long long)gridDim.x - 1ull;
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            if (threadIdx.x < a.n_ranks) {
-                unsigned long long c = atomicExch((unsigned long long*)&a.d_send_state[a.parity * 64 + threadIdx.x], 0ull);
-                if (c > (unsigned long long)a.seg_capacity) c = (unsigned long long)a.seg_capacity;
-                a.d_peer_bufs[threadIdx.x][XHDR_SEG_COUNTS + a.parity * 64 + a.rank] = c;
-                __threadfence_system();
-            }
-            if (threadIdx.x == 0) a.d_send_state[128 + a.parity] = 0;
-        }
-    }
-}
-
 // K5: insert keys into the open-addressing visited table (EMPTY = all ones).  New keys are
 // appended to d_out_keys through the cursor d_counts[0]; d_counts[1] counts won successors seen,
 // d_counts[2] is set when the table is full.
 __global__ void __launch_bounds__(256) bfs_hash_insert_kernel(const ts_bfs_args a) {
-    // sender-partitioned inbox (d_seg_counts): the items are the first d_seg_counts[s] keys of each of
-    // the n_ranks segments of seg_capacity keys, taken in segment order
-    __shared__ int64_t seg_start[65];
-    if (a.d_seg_counts) {
-        if (threadIdx.x == 0) {
-            int64_t acc = 0;
-            for (int s = 0; s < a.n_ranks; ++s) {
-                seg_start[s] = acc;
-                const int64_t c = (int64_t)a.d_seg_counts[s];
-                acc += c < a.seg_capacity ? c : a.seg_capacity;
-            }
-            seg_start[a.n_ranks] = acc;
-        }
-        __syncthreads();
-    }
-    const int64_t n_items = a.d_seg_counts ? seg_start[a.n_ranks] : item_count(a);
+    const int64_t n_items = item_count(a);
     const unsigned lane = threadIdx.x & 31u;
     // grid-stride over whole blocks of 256 items, so every warp runs the same number of rounds
     for (int64_t base = (int64_t)blockIdx.x * 256; base < n_items; base += (int64_t)gridDim.x * 256) {
     const int64_t i = base + threadIdx.x;
-    uint64_t raw = BFS_NONE;
-    if (i < n_items) {
-        if (a.d_seg_counts) {
-            int s = 0;
-            while (i >= seg_start[s + 1]) ++s;
-            raw = a.d_in_keys[(int64_t)s * a.seg_capacity + (i - seg_start[s])];
-        } else {
-            raw = a.d_in_keys[i];
-        }
-    }
+    const uint64_t raw = i < n_items ? a.d_in_keys[i] : BFS_NONE;
     const bool live = raw != BFS_NONE;
     const uint64_t key = raw & ~BFS_WON_BIT;
     bool is_new = false, full = false;
@@ -576,7 +446,6 @@ template <int S> static cudaError_t bfs_dispatch_T(int op, const ts_bfs_args& a,
     case T:                                                                             \
         if (op == 0) bfs_seed_kernel<S, T><<<blocks, 256, 0, st>>>(a);                  \
         else if (op == 1) bfs_expand_kernel<S, T><<<blocks, 256, 0, st>>>(a);           \
-        else if (op == 3 && a.xchg_staged) bfs_expand_exchange_staged_kernel<S, T><<<blocks ? blocks : 1u, 256, 0, st>>>(a);  \
         else if (op == 3) bfs_expand_exchange_kernel<S, T><<<blocks, 256, 0, st>>>(a);  \
         else if (op == 4) bfs_trace_step_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
         else bfs_traceback_kernel<S, T><<<(unsigned)((a.n_items + 127) / 128), 128, 0, st>>>(a); \
@@ -639,11 +508,8 @@ int ts_bfs_expand(const ts_bfs_args* a, void* stream) {
 int ts_bfs_expand_exchange(const ts_bfs_args* a, void* stream) {
     if (int rc = bfs_check(a, true)) return rc;
     if (a->n_ranks < 1 || a->n_ranks > 64 || a->inbox_capacity < 1 || (a->parity != 0 && a->parity != 1)) return TS_E_BAD_ARGUMENT;
-    if (a->seg_capacity < 0 || a->rank < 0 || a->rank >= a->n_ranks) return TS_E_BAD_ARGUMENT;
-    if (a->seg_capacity > 0 && (!a->xchg_staged || !a->d_send_state || a->seg_capacity * a->n_ranks > a->inbox_capacity)) return TS_E_BAD_ARGUMENT;
-    // sender-partitioned: a rank with nothing to send still publishes its (zero) segment counts
-    if (a->n_items == 0 && a->seg_capacity == 0) return 0;
-    if (!a->d_walls || !a->d_targets_packed || !a->d_counts || !a->d_peer_bufs || (a->n_items && !a->d_in_keys)) return TS_E_NULL_POINTER;
+    if (a->n_items == 0) return 0;
+    if (!a->d_walls || !a->d_targets_packed || !a->d_in_keys || !a->d_counts || !a->d_peer_bufs) return TS_E_NULL_POINTER;
     return (int)bfs_dispatch(3, *a, (cudaStream_t)stream);
 }
 
@@ -722,9 +588,8 @@ int ts_bfs_hash_insert(const ts_bfs_args* a, void* stream) {
     if (a->table_capacity < 2 || (a->table_capacity & (a->table_capacity - 1))) return TS_E_BAD_ARGUMENT;
     if (a->n_items == 0) return 0;
     if (!a->d_in_keys || !a->d_counts || !a->d_out_keys || !a->d_table) return TS_E_NULL_POINTER;
-    if (a->d_seg_counts && (a->seg_capacity < 1 || a->n_ranks < 1 || a->n_ranks > 64)) return TS_E_BAD_ARGUMENT;
     unsigned blocks = (unsigned)((a->n_items + 255) / 256);
-    if ((a->d_n_items || a->d_seg_counts) && blocks > BFS_PERSISTENT_BLOCKS) blocks = BFS_PERSISTENT_BLOCKS;
+    if (a->d_n_items && blocks > BFS_PERSISTENT_BLOCKS) blocks = BFS_PERSISTENT_BLOCKS;
     bfs_hash_insert_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
