@@ -76,10 +76,12 @@ def main() -> int:
     phases = None
     if args.profile and args.mode == "hash":
         solver.profile = True
-        solver.solve()
+        res_p = solver.solve()          # host-driven levels (a read-back per level): must find the same search
         phases = {k: round(v, 4) for k, v in solver.phase_seconds.items()}
+        phases["same_search"] = bool(res_p.levels == res.levels and res_p.generated == res.generated and
+                                     torch.equal(res_p.states_per_puzzle, res.states_per_puzzle))
 
-    ok = True
+    ok = phases is None or phases["same_search"]
     if rank == 0 and args.check:
         from oracle import oracle as orc
         S = args.size
