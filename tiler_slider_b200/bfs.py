@@ -8,14 +8,24 @@ set is an open-addressing hash table in HBM.  BFS itself is defined by this repo
 unpinned); level histograms are pinned to a plain BFS over the reference's move
 (tests/golden/misc.json).
 
-Multi-GPU: every rank holds the (small, static) puzzle table and the slice of the visited set
-whose keys hash to it.  One exchange per depth:
-    expand local frontier (K4)  ->  bucket successors by owner rank  ->  all_to_all_single of
-    the bucket sizes, then of the u64 keys (NCCL over NVLink)  ->  insert into the local table
-    (K5); the keys that were new form the next local frontier  ->  all_reduce of the new-state
-    count (termination) and of the goal flag.
-A single puzzle has a tiny state space (51-950 states for real 6x6 levels), so the
-exchange only pays off for a batch of puzzles; key = puzzle id || canonical positions.
+Two searches, same results (states per puzzle, level histogram, solve depths, shortest move strings):
+
+* `LocalBfs` (K6, csrc/ts_bfs_local.cu): a batch of small puzzles (size <= 8, up to 4 tiles), one CTA
+  per puzzle, visited set and frontier in shared memory; puzzles sharded over the ranks by index,
+  nothing exchanged.  Puzzles that outgrow the chip fall back to the search below.
+* `BfsSolver`: one visited table in HBM, hash-partitioned over the ranks -- every rank holds the
+  (small, static) puzzle table and the slice of the visited set whose keys hash to it; key = puzzle
+  id || canonical positions.  One exchange per depth, either fused into the expansion (K4x: the
+  successors go straight into the owners' inboxes through NVLink peer memory, levels separated by
+  an 8-byte all-reduce) or as
+      expand local frontier (K4)  ->  bucket successors by owner rank  ->  all_gather of the
+      bucket sizes, all_to_all_single of the u64 keys (NCCL)  ->  insert into the local table (K5);
+      the keys that were new form the next local frontier; a level in which nobody sent anything
+      ends the search.
+  Single-rank and peer-memory searches keep the frontier sizes on the device and launch 16 levels
+  between host read-backs.  with_paths records parents (over several ranks they travel with the
+  keys) and walks the chains back from the recorded last link of every solution.
+`solve_batch` picks the search that fits a batch.
 
 The device kernels sit behind `CudaBfsKernels`; tests run the same driver logic on CPU
 tensors over gloo with a CPU stand-in for the kernels (tests/test_bfs_gloo.py).

@@ -16,7 +16,10 @@
 // bfs_partition_count / bfs_partition_scatter (bucket successors by owner rank =
 // hash(key) % n_ranks, ahead of the NCCL all-to-all done by the Python driver), K5
 // bfs_hash_insert (open-addressing visited table, atomicCAS; emits the new keys = next
-// frontier).
+// frontier; optionally per-puzzle tallies, parent links and the goal successor of every puzzle),
+// K4x bfs_expand_exchange (expand + bucket + store into the owners' inboxes over NVLink peer
+// memory, one kernel), bfs_traceback / bfs_trace_step (shortest move strings from the parent links:
+// on one rank / one step at a time when the links are spread over the owners).
 #include "ts_common.cuh"
 #include "../../include/tiler_slider.h"
 
